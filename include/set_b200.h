@@ -1,0 +1,175 @@
+/*
+ * set_b200.h -- C ABI of the B200-native EditNet/DCNet decode path.
+ *
+ * The reference (fawazsammani/show-edit-tell) has no FFI/plugin layer: its hot path sits
+ * behind `nn.Module.forward` methods.  This header is the boundary a
+ * binding would target instead: stateless functions over caller-owned, contiguous device
+ * buffers (fp32 data, int64 tokens/lengths exactly as the reference's tensors hold them),
+ * explicit sizes, an explicit CUDA stream, caller-provided workspace.  No torch types.
+ * Every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - matrices are row-major [out_features, in_features] exactly like `nn.Linear.weight`;
+ *   - E = D = C (emb_dim = decoder_dim = caption_features_dim), which the reference's own
+ *     concatenations force (editnet.py:359-361,468-469); A = attention_dim, F = image
+ *     feature dim, V = vocabulary size.  D, A, F must be multiples of 4;
+ *   - rows of a batch are in the order the reference computes in: sorted by caption
+ *     length, descending, for the teacher-forced path (editnet.py:488-492); caller order
+ *     for the rollout path (editnet_rl.py:485-549);
+ *   - return value 0 = success; otherwise set_last_error() describes the failure.  The
+ *     library never falls back to a CPU path.
+ */
+#ifndef SET_B200_H_
+#define SET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SET_API __attribute__((visibility("default")))
+#else
+#define SET_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SetDims {
+  int V; /* vocabulary (len(word_map)) */
+  int D; /* emb_dim = decoder_dim = caption_features_dim (1024) */
+  int A; /* attention_dim (512) */
+  int F; /* image_features_dim (2048) */
+} SetDims;
+
+/* EditNet parameters, one pointer per `state_dict` entry of DecoderC
+ * (editnet.py:451-471; key names in SURVEY.md Appendix B).  The same struct, pointing
+ * at gradient buffers, receives d(loss)/d(param) from the backward entry points
+ * (accumulated: the caller zeroes them). */
+typedef struct SetEditNetParams {
+  float* embed;                          /* embed.embedding.weight                  [V,D]      */
+  float *enc_x2h_w, *enc_x2h_b;          /* caption_encoder.lstm_encoder_cell.x2h   [4D,D],[4D]*/
+  float *enc_h2h_w, *enc_h2h_b;          /* caption_encoder.lstm_encoder_cell.h2h   [4D,D],[4D]*/
+  float *enc_aff_w, *enc_aff_b;          /* caption_encoder.affine_hn               [D,D],[D]  */
+  float *ca_feat_w, *ca_feat_b;          /* caption_attention.cap_features_att      [A,D],[A]  */
+  float *ca_dec_w, *ca_dec_b;            /* caption_attention.cap_decoder_att       [A,D],[A]  */
+  float *ca_full_w, *ca_full_b;          /* caption_attention.cap_full_att          [1,A],[1]  */
+  float *ca_gate_w, *ca_gate_b;          /* caption_attention.context_gate          [D,3D],[D] */
+  float *ca_sc_w, *ca_sc_b;              /* caption_attention.sc_affine             [D,D],[D]  */
+  float *ca_tc_w, *ca_tc_b;              /* caption_attention.tc_affine             [D,2D],[D] */
+  float *va_emb_w, *va_emb_b;            /* visual_attention.att_embed.0            [D,F],[D]  */
+  float *va_feat_w, *va_feat_b;          /* visual_attention.features_att           [A,D],[A]  */
+  float *va_dec_w, *va_dec_b;            /* visual_attention.decoder_att            [A,D],[A]  */
+  float *va_full_w, *va_full_b;          /* visual_attention.full_att               [1,A],[1]  */
+  float *al_wih, *al_whh, *al_bih, *al_bhh; /* attention_lstm.{weight_ih [4D,3D+F], weight_hh [4D,D], bias_*} */
+  float *cl_x2h_w, *cl_x2h_b;            /* copy_lstm.x2h                           [4D,2D+F]  */
+  float *cl_h2h_w, *cl_h2h_b;            /* copy_lstm.h2h                           [4D,D]     */
+  float *cl_gcn_w, *cl_gcn_b;            /* copy_lstm.gate_cnew                     [D,D]      */
+  float *cl_gcm_w, *cl_gcm_b;            /* copy_lstm.gate_cmem                     [D,D]      */
+  float *fc_w, *fc_b;                    /* fc                                      [V,D],[V]  */
+} SetEditNetParams;
+
+/* Shape of one teacher-forced (XE) or rollout call. */
+typedef struct SetSeqShape {
+  int B;        /* captions in the batch                                                  */
+  int R;        /* regions per image (36; <=128)                                          */
+  int Wc;       /* width of the caption tensor (20)      -- XE only                       */
+  int Wp;       /* width of the previous-caption tensor (18)                              */
+  int P;        /* max previous-caption length in the batch (encoder steps, <=Wp)         */
+  int T;        /* decode steps: max(decode_lengths) for XE, max_len for rollouts         */
+  int train;    /* 1: dropout active (Philox keyed by `seed`), 0: eval                    */
+  int adaptive; /* 1: ragged-region variant (adaptive_features/editnet_adaptive.py:438-457):
+                   all-zero region rows are padding, image_mean is an input              */
+} SetSeqShape;
+
+SET_API const char* set_last_error(void);
+SET_API int set_version(void);
+
+/* Workspace (saved activations + scratch) needed by set_editnet_xe_forward/backward and
+ * by set_editnet_rollout for this shape. */
+SET_API size_t set_editnet_workspace_bytes(const SetDims* dims, const SetSeqShape* shape);
+
+/* Teacher-forced forward: replaces DecoderC.forward, editnet.py:479-548 (use_ss=False)
+ * and, with shape->adaptive, adaptive_features/editnet_adaptive.py:489-562.
+ *   feats            [B,R,F]   image_features[sort_ind]
+ *   image_mean       [B,F]     adaptive only (else NULL: computed as feats.mean(1), editnet.py:503)
+ *   caps             [B,Wc]    encoded_captions[sort_ind] (int64)
+ *   decode_len_host  [B]       HOST ints, caption_lengths-1, non-increasing (editnet.py:497)
+ *   prev, prev_len   [B,Wp],[B] encoded_previous_captions / previous_cap_length, sorted rows (int64)
+ *   predictions      [B,T,V]   written in full: rows t >= decode_len[i] are zero (editnet.py:499,546)
+ * The workspace keeps what set_editnet_xe_backward needs; it must stay untouched between
+ * the two calls. */
+SET_API int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                           const float* feats, const float* image_mean, const int64_t* caps,
+                           const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                           uint64_t seed, float* predictions, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Backward of the above for an upstream gradient d_predictions [B,T,V] (entries at
+ * t >= decode_len[i] are ignored, as the reference's slice-assignment does).  Replaces the
+ * autograd replay that `loss.backward()` (editnet.py:579) performs through DecoderC.forward.
+ * Gradients are ACCUMULATED into *grads. */
+SET_API int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                            const SetEditNetParams* grads, const float* feats, const int64_t* caps,
+                            const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                            uint64_t seed, const float* d_predictions, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Packed cross-entropy over the decoded positions: replaces pack_padded_sequence x2 +
+ * CrossEntropyLoss, editnet.py:571-577.  Writes the mean loss to loss_out[0],
+ * sum(decode_len) to loss_out[1], and (if d_predictions != NULL) d(mean loss)/d(predictions)
+ * -- zero at undecoded positions; may alias `predictions`.  `inv_count` <= 0 means
+ * 1/sum(decode_len); data-parallel callers pass 1/global_count instead. */
+SET_API int set_xe_loss(int B, int T, int V, int Wc, const float* predictions, const int64_t* caps,
+                const int* decode_len_dev, float inv_count, float* loss_out, float* d_predictions,
+                void* stream);
+
+/* Autoregressive rollout: replaces DecoderC.forward of editnet_rl.py:485-549.
+ *   mode 0 = greedy (sample_max, :521), 1 = multinomial sample (sample_rl, :525-527; inverse-CDF
+ *   on Philox uniforms keyed by `seed`), 2 = forced (replay `forced` [B,T] tokens and return
+ *   their log-probs; used to validate mode 1 and to re-materialise activations).
+ *   seq [B,T] int64 and seq_logprobs [B,T] are written in full (zeros after a row finishes).
+ * With shape->train the activations for set_editnet_rollout_backward are kept in the workspace. */
+SET_API int set_editnet_rollout(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                        const float* feats, const float* image_mean, const int64_t* prev,
+                        const int64_t* prev_len, int64_t start_token, int64_t end_token, int mode,
+                        const int64_t* forced, uint64_t seed, int64_t* seq, float* seq_logprobs,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of a rollout for upstream d(loss)/d(seq_logprobs) [B,T] (RewardCriterion,
+ * editnet_rl.py:557-573, produces it).  Gradients are accumulated into *grads. */
+SET_API int set_editnet_rollout_backward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                                 const SetEditNetParams* grads, const float* feats, const int64_t* prev,
+                                 const int64_t* prev_len, uint64_t seed, const float* d_seq_logprobs,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* SCST loss: replaces RewardCriterion.forward, editnet_rl.py:557-573.  loss_out[0] = loss;
+ * d_logprobs [B,T] (optional) = d loss / d seq_logprobs. */
+SET_API int set_reward_criterion(int B, int T, const float* seq_logprobs, const int64_t* seq, const float* reward,
+                         float* loss_out, float* d_logprobs, void* stream);
+
+/* Global-norm clip + Adam over one flat parameter buffer: replaces clip_grad_norm_(0.25) +
+ * Adam.step(), editnet.py:580-581.  Gradients are first multiplied by grad_scale and, when
+ * count_dev != NULL, divided by *count_dev (a device float: the all-reduced token count of a
+ * data-parallel step whose ranks contributed loss SUMS).  `scratch` holds >= 4
+ * floats; scratch[1] receives the pre-clip total norm. */
+SET_API int set_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                  int step, float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                  const float* count_dev, float* scratch, void* stream);
+
+/* Test / debugging helpers. */
+/* keep flags (0/1 floats) of dropout site `site` (1 enc-embed, 2 embed, 3 att_embed, 4 fc) for
+ * linear element indices [base, base+n) -- the exact bits the kernels use. */
+SET_API int set_dropout_keep_mask(float* out, size_t n, uint64_t seed, int site, size_t base, void* stream);
+/* byte offset and byte size of a named workspace buffer for this shape (returns 0 if found). */
+SET_API int set_editnet_workspace_lookup(const SetDims* dims, const SetSeqShape* shape, const char* name,
+                                 size_t* offset, size_t* bytes);
+/* C = A @ B^T style contraction through the library's GEMM engine (mode 0 NT, 1 NN, 2 TN). */
+SET_API int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,
+             const float* bias, float* C, long ldc, int beta, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SET_B200_H_ */

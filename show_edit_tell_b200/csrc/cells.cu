@@ -1,0 +1,726 @@
+// Element-wise / attention kernels of the decode step.  See cells.cuh for the contract
+// of each launcher and the reference lines it reproduces.
+#include "cells.cuh"
+
+namespace set {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int blocks_for(long n, int per_block) {
+  long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)b;
+}
+
+// four keep bits for elements idx..idx+3 (idx % 4 == 0)
+__device__ __forceinline__ uint32_t drop_keep4(uint64_t seed, uint32_t site, uint64_t idx) {
+  const uint4 b = drop_bits128(seed, site, idx >> 7);
+  const uint32_t bit = (uint32_t)idx & 127u;
+  const uint32_t w = bit < 64 ? (bit < 32 ? b.x : b.y) : (bit < 96 ? b.z : b.w);
+  return (w >> (bit & 31u)) & 0xFu;
+}
+
+// ------------------------------------------------------------------------ embedding
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ tokens, long tok_ld, long tok_os,
+                                 const float* __restrict__ table, int V, float* __restrict__ out, int n_outer,
+                                 int n_inner, int D, int train, uint64_t seed, uint32_t site, long drop_row0,
+                                 long drop_os, long drop_is) {
+  const int D4 = D >> 2;
+  const long total = (long)n_outer * n_inner * D4;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int e4 = (int)(x % D4);
+    const long row = x / D4;
+    const int i = (int)(row % n_inner), o = (int)(row / n_inner);
+    long tok = tokens[(long)i * tok_ld + (long)o * tok_os];
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    float4 v = __ldg(reinterpret_cast<const float4*>(table + tok * D) + e4);
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    if (train) {
+      const uint64_t idx = (uint64_t)(drop_row0 + (long)o * drop_os + (long)i * drop_is) * D + (uint64_t)e4 * 4;
+      const uint32_t k = drop_keep4(seed, site, idx);
+      v.x = (k & 1) ? v.x * 2.f : 0.f; v.y = (k & 2) ? v.y * 2.f : 0.f;
+      v.z = (k & 4) ? v.z * 2.f : 0.f; v.w = (k & 8) ? v.w * 2.f : 0.f;
+    }
+    reinterpret_cast<float4*>(out + row * D)[e4] = v;
+  }
+}
+
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ tokens, long tok_ld, long tok_os,
+                                 const float* __restrict__ out, const float* __restrict__ dout,
+                                 float* __restrict__ table_grad, int V, int n_outer, int n_inner, int D,
+                                 float scale, const int* __restrict__ row_len) {
+  const long total = (long)n_outer * n_inner * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int e = (int)(x % D);
+    const long row = x / D;
+    const int i = (int)(row % n_inner), o = (int)(row / n_inner);
+    if (row_len && row_len[i] <= o) continue;
+    if (out[x] > 0.f) {
+      const float g = dout[x] * scale;
+      long tok = tokens[(long)i * tok_ld + (long)o * tok_os];
+      tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+      if (g != 0.f) atomicAdd(table_grad + tok * D + e, g);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------- region prep
+__global__ void region_mean_kernel(const float* __restrict__ feats, float* __restrict__ out, int B, int R, int F) {
+  const long total = (long)B * F;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int f = (int)(x % F);
+    const long i = x / F;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += feats[(i * R + r) * F + f];
+    out[x] = s / (float)R;
+  }
+}
+
+__global__ void region_count_kernel(const float* __restrict__ feats, int* __restrict__ nreg, int R, int F) {
+  // one block per sample; warp per region row
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int i = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = wid; r < R; r += nw) {
+    float s = 0.f;
+    for (int f = lane; f < F; f += 32) s += feats[((long)i * R + r) * F + f];
+    s = warp_sum(s);
+    if (lane == 0 && s != 0.f) atomicAdd(&cnt, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) nreg[i] = cnt;
+}
+
+__global__ void zero_pad_regions_kernel(float* __restrict__ fe, const int* __restrict__ nreg, int B, int R, int D) {
+  const long total = (long)B * R * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const long row = x / D;
+    const int r = (int)(row % R), i = (int)(row / R);
+    if (r >= nreg[i]) fe[x] = 0.f;
+  }
+}
+
+__global__ void vis_dropout_fwd_kernel(const float* __restrict__ fe_pre, float* __restrict__ fe_t, int T, long n,
+                                       uint64_t seed) {
+  // n = B*R*D (multiple of 4); fe_t[t][x]
+  const long n4 = n >> 2;
+  const long total = (long)T * n4;
+  for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < total; y += (long)gridDim.x * blockDim.x) {
+    const long x4 = y % n4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(fe_pre) + x4);
+    const uint32_t k = drop_keep4(seed, kSiteVis, (uint64_t)y * 4);
+    v.x = (k & 1) ? v.x * 2.f : 0.f; v.y = (k & 2) ? v.y * 2.f : 0.f;
+    v.z = (k & 4) ? v.z * 2.f : 0.f; v.w = (k & 8) ? v.w * 2.f : 0.f;
+    reinterpret_cast<float4*>(fe_t)[y] = v;
+  }
+}
+
+__global__ void vis_dropout_bwd_kernel(const float* __restrict__ fe_pre, const float* __restrict__ dfe_t,
+                                       float* __restrict__ dfe_pre, const int* __restrict__ dec_len, int T, int B,
+                                       long per_sample, uint64_t seed) {
+  // per_sample = R*D (multiple of 4)
+  const long ps4 = per_sample >> 2;
+  const long total = (long)B * ps4;
+  for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < total; y += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(y / ps4);
+    const float4 f = __ldg(reinterpret_cast<const float4*>(fe_pre) + y);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int Ti = dec_len ? min(dec_len[i], T) : T;
+    for (int t = 0; t < Ti; ++t) {
+      const long z = (long)t * total + y;
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dfe_t) + z);
+      const uint32_t k = drop_keep4(seed, kSiteVis, (uint64_t)z * 4);
+      if (k & 1) acc.x += d.x; if (k & 2) acc.y += d.y; if (k & 4) acc.z += d.z; if (k & 8) acc.w += d.w;
+    }
+    acc.x = f.x > 0.f ? acc.x * 2.f : 0.f; acc.y = f.y > 0.f ? acc.y * 2.f : 0.f;
+    acc.z = f.z > 0.f ? acc.z * 2.f : 0.f; acc.w = f.w > 0.f ? acc.w * 2.f : 0.f;
+    reinterpret_cast<float4*>(dfe_pre)[y] = acc;
+  }
+}
+
+__global__ void relu_bwd_kernel(float* __restrict__ dx, const float* __restrict__ y, long n) {
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x)
+    if (!(y[x] > 0.f)) dx[x] = 0.f;
+}
+__global__ void tanh_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long n) {
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) {
+    const float v = y[x];
+    dy[x] *= (1.f - v * v);
+  }
+}
+
+// ------------------------------------------------------------------------ LSTM cells
+__global__ void lstm_fwd_kernel(const float* __restrict__ pre, long ld_pre, const float* __restrict__ c_prev,
+                                const float* __restrict__ h_prev, float* __restrict__ gates,
+                                float* __restrict__ c_out, float* __restrict__ h_out, long ld_h, int rows, int D,
+                                const int64_t* __restrict__ len, int t, float* __restrict__ seq_h,
+                                float* __restrict__ seq_m, long seq_ld) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    const float* p = pre + i * ld_pre;
+    const bool active = (len == nullptr) || (len[i] > t);
+    float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c, h;
+    if (active) {
+      gi = sigmoidf_(p[d]); gf = sigmoidf_(p[D + d]); gg = tanhf(p[2 * D + d]); go = sigmoidf_(p[3 * D + d]);
+      c = gf * c_prev[x] + gi * gg;
+      h = go * tanhf(c);
+    } else {
+      c = c_prev[x];
+      h = h_prev[x];
+    }
+    float* g = gates + i * 4 * D;
+    g[d] = gi; g[D + d] = gf; g[2 * D + d] = gg; g[3 * D + d] = go;
+    c_out[x] = c;
+    h_out[i * ld_h + d] = h;
+    if (seq_h) {
+      seq_h[i * seq_ld + (long)t * D + d] = active ? h : 0.f;
+      seq_m[i * seq_ld + (long)t * D + d] = active ? c : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void lstm_bwd_core(float gi, float gf, float gg, float go, float c_prev, float c_cur,
+                                              float dh, float dc_in, float* dg, int D, int d, float& dc_prev) {
+  const float tc = tanhf(c_cur);
+  const float dc = dc_in + dh * go * (1.f - tc * tc);
+  dg[d] = dc * gg * gi * (1.f - gi);
+  dg[D + d] = dc * c_prev * gf * (1.f - gf);
+  dg[2 * D + d] = dc * gi * (1.f - gg * gg);
+  dg[3 * D + d] = dh * tc * go * (1.f - go);
+  dc_prev = dc * gf;
+}
+
+__global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                const float* __restrict__ c_cur, const float* __restrict__ dh, long ld_dh,
+                                const float* __restrict__ dh_b, float* __restrict__ dc_carry,
+                                float* __restrict__ dgates, int rows, int D) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    const float* g = gates + i * 4 * D;
+    float dhv = dh[i * ld_dh + d];
+    if (dh_b) dhv += dh_b[x];
+    float dcp;
+    lstm_bwd_core(g[d], g[D + d], g[2 * D + d], g[3 * D + d], c_prev[x], c_cur[x], dhv, dc_carry[x],
+                  dgates + i * 4 * D, D, d, dcp);
+    dc_carry[x] = dcp;
+  }
+}
+
+__global__ void enc_lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                    const float* __restrict__ c_cur, float* __restrict__ dh_run,
+                                    float* __restrict__ dc_run, const float* __restrict__ dseq_h,
+                                    const float* __restrict__ dseq_m, long seq_ld,
+                                    const float* __restrict__ dh_last, const int64_t* __restrict__ len, int t,
+                                    float* __restrict__ dgates, int rows, int D) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    float* dg = dgates + i * 4 * D;
+    const long L = len[i];
+    if (L <= t) {
+      dg[d] = 0.f; dg[D + d] = 0.f; dg[2 * D + d] = 0.f; dg[3 * D + d] = 0.f;
+      continue;
+    }
+    const float* g = gates + i * 4 * D;
+    float dhv = dh_run[x] + dseq_h[i * seq_ld + (long)t * D + d];
+    if (L - 1 == t) dhv += dh_last[x];
+    const float dcv = dc_run[x] + dseq_m[i * seq_ld + (long)t * D + d];
+    float dcp;
+    lstm_bwd_core(g[d], g[D + d], g[2 * D + d], g[3 * D + d], c_prev[x], c_cur[x], dhv, dcv, dg, D, d, dcp);
+    dc_run[x] = dcp;
+  }
+}
+
+__global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restrict__ mask, long rows, int D) {
+  // warp per (i,p) row
+  const int lane = threadIdx.x & 31;
+  const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= rows) return;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s += prev_m[w * D + d];
+  s = warp_sum(s);
+  if (lane == 0) mask[w] = (s != 0.f) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------ attention
+// dynamic smem: a2[A] | wv[A] | sc[max(P,R)] | red[40]
+__global__ void __launch_bounds__(kThreads) attention_fwd_kernel(const AttnFwdArgs a) {
+  extern __shared__ float sm[];
+  const int A = a.A;
+  float* a2 = sm;
+  float* wv = sm + A;
+  float* sc = sm + 2 * A;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const bool cap = (blockIdx.y == 0);
+  if (cap && a.att1c == nullptr) return;
+  if (!cap && a.att1v == nullptr) return;
+  const int n = cap ? a.P : a.R;
+  const float* att1 = cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A;
+  const float* s2row = a.s2 + (long)i * a.ld_s2 + (cap ? 0 : A);
+  const float* w = cap ? a.cap_w : a.vis_w;
+  const float bias = cap ? a.cap_b[0] : a.vis_b[0];
+  for (int x = tid; x < A; x += blockDim.x) { a2[x] = s2row[x]; wv[x] = w[x]; }
+  __syncthreads();
+  const int nvalid = cap ? n : (a.nreg ? a.nreg[i] : n);
+  for (int j = wid; j < n; j += nw) {
+    float s = 0.f;
+    const float* row = att1 + (long)j * A;
+    if (cap) {
+      for (int x = lane; x < A; x += 32) s += wv[x] * tanhf(row[x] + a2[x]);
+    } else {
+      for (int x = lane; x < A; x += 32) s += wv[x] * fmaxf(row[x] + a2[x], 0.f);
+    }
+    s = warp_sum(s) + bias;
+    if (cap) { if (a.mask[(long)i * a.P + j] == 0.f) s = kNegFill; }
+    else if (j >= nvalid) s = kNegFill;
+    if (lane == 0) sc[j] = s;
+  }
+  __syncthreads();
+  // softmax (+ argmax) by warp 0
+  if (wid == 0) {
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sc[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) { const float e = expf(sc[j] - m); sc[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int j = lane; j < n; j += 32) sc[j] = sc[j] / sum;
+  }
+  __syncthreads();
+  float* alpha_out = cap ? a.alpha_c + (long)i * a.P : a.alpha_v + (long)i * a.R;
+  for (int j = tid; j < n; j += blockDim.x) alpha_out[j] = sc[j];
+  if (cap) {
+    const float* ph = a.prev_h + (long)i * a.P * a.D;
+    for (int d = tid; d < a.D; d += blockDim.x) {
+      float c = 0.f;
+      for (int j = 0; j < n; ++j) c += sc[j] * ph[(long)j * a.D + d];
+      a.ctx[(long)i * a.D + d] = c;
+    }
+    if (a.prev_m) {
+      int js = 0; float best = sc[0];
+      for (int j = 1; j < n; ++j) if (sc[j] > best) { best = sc[j]; js = j; }
+      const float wsel = best + (1.f - best);
+      const float* pm = a.prev_m + ((long)i * a.P + js) * a.D;
+      for (int d = tid; d < a.D; d += blockDim.x) a.sel[(long)i * a.D + d] = wsel * pm[d];
+      if (tid == 0) a.sel_idx[i] = js;
+    }
+  } else {
+    const float* ft = a.feats + (long)i * a.R * a.F;
+    float* out = a.att_img + (long)i * a.ld_img;
+    const int F4 = a.F >> 2;
+    for (int f4 = tid; f4 < F4; f4 += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < nvalid; ++r) {
+        const float al = sc[r];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(ft + (long)r * a.F) + f4);
+        acc.x += al * v.x; acc.y += al * v.y; acc.z += al * v.z; acc.w += al * v.w;
+      }
+      reinterpret_cast<float4*>(out)[f4] = acc;
+    }
+  }
+}
+
+// dynamic smem: a2[A] | wv[A] | al[n] | dal[n] | ds[n] | red[40]
+__global__ void __launch_bounds__(kThreads) attention_bwd_kernel(const AttnBwdArgs a) {
+  extern __shared__ float sm[];
+  const int A = a.A;
+  const bool cap = (blockIdx.y == 0);
+  if (cap && a.att1c == nullptr) return;
+  if (!cap && a.att1v == nullptr) return;
+  const int n = cap ? a.P : a.R;
+  float* a2 = sm;
+  float* wv = sm + A;
+  float* al = sm + 2 * A;
+  float* dal = al + n;
+  float* ds = dal + n;
+  float* red = ds + n;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const float* s2row = a.s2 + (long)i * a.ld_s2 + (cap ? 0 : A);
+  const float* w = cap ? a.cap_w : a.vis_w;
+  const float* alpha = cap ? a.alpha_c + (long)i * a.P : a.alpha_v + (long)i * a.R;
+  for (int x = tid; x < A; x += blockDim.x) { a2[x] = s2row[x]; wv[x] = w[x]; }
+  for (int j = tid; j < n; j += blockDim.x) al[j] = alpha[j];
+  __syncthreads();
+  const int nvalid = cap ? n : (a.nreg ? a.nreg[i] : n);
+  const int js = (cap && a.dsel) ? a.sel_idx[i] : -1;
+  // d alpha_j = <dcontext, value_j> (+ select term)
+  if (cap) {
+    const float* ph = a.prev_h + (long)i * a.P * a.D;
+    const float* dc = a.dctx + (long)i * a.D;
+    for (int j = wid; j < n; j += nw) {
+      float s = 0.f;
+      for (int d = lane; d < a.D; d += 32) s += dc[d] * ph[(long)j * a.D + d];
+      if (j == js) {
+        const float* pm = a.prev_m + ((long)i * a.P + j) * a.D;
+        const float* dsl = a.dsel + (long)i * a.D;
+        for (int d = lane; d < a.D; d += 32) s += dsl[d] * pm[d];
+      }
+      s = warp_sum(s);
+      if (lane == 0) dal[j] = s;
+    }
+  } else {
+    const float* ft = a.feats + (long)i * a.R * a.F;
+    const float* di = a.datt_img + (long)i * a.ld_dimg;
+    for (int r = wid; r < n; r += nw) {
+      float s = 0.f;
+      if (r < nvalid)
+        for (int f = lane; f < a.F; f += 32) s += di[f] * ft[(long)r * a.F + f];
+      s = warp_sum(s);
+      if (lane == 0) dal[r] = s;
+    }
+  }
+  __syncthreads();
+  // softmax backward
+  float part = 0.f;
+  for (int j = tid; j < n; j += blockDim.x) part += al[j] * dal[j];
+  const float dot = block_sum(part, red);
+  float dsum = 0.f;
+  for (int j = tid; j < n; j += blockDim.x) {
+    float v = al[j] * (dal[j] - dot);
+    if (cap) { if (a.mask[(long)i * a.P + j] == 0.f) v = 0.f; }
+    else if (j >= nvalid) v = 0.f;
+    ds[j] = v;
+    dsum += v;
+  }
+  const float dbias = block_sum(dsum, red);  // also orders ds[] writes before the reads below
+  if (tid == 0) atomicAdd(cap ? a.dcap_b : a.dvis_b, dbias);
+  // value gradients
+  if (cap) {
+    const float* dc = a.dctx + (long)i * a.D;
+    float* dph = a.dprev_h + (long)i * a.P * a.D;
+    for (int d = tid; d < a.D; d += blockDim.x) {
+      const float g = dc[d];
+      for (int j = 0; j < n; ++j) dph[(long)j * a.D + d] += al[j] * g;
+    }
+    if (js >= 0) {
+      const float best = al[js];
+      const float wsel = best + (1.f - best);
+      float* dpm = a.dprev_m + ((long)i * a.P + js) * a.D;
+      const float* dsl = a.dsel + (long)i * a.D;
+      for (int d = tid; d < a.D; d += blockDim.x) dpm[d] += wsel * dsl[d];
+    }
+  }
+  // score-MLP backward: thread per attention unit
+  const float* att1 = cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A;
+  float* datt1 = cap ? a.datt1c + (long)i * a.P * A : a.datt1v + (long)i * a.R * A;
+  const bool accum = cap ? true : (a.datt1v_accum != 0);
+  float* ds2row = a.ds2 + (long)i * a.ld_ds2 + (cap ? 0 : A);
+  float* dwv = cap ? a.dcap_w : a.dvis_w;
+  for (int x = tid; x < A; x += blockDim.x) {
+    float d2 = 0.f, dw = 0.f;
+    const float av = a2[x], wx = wv[x];
+    for (int j = 0; j < n; ++j) {
+      const float pre = att1[(long)j * A + x] + av;
+      float y, dpre;
+      if (cap) { y = tanhf(pre); dpre = ds[j] * wx * (1.f - y * y); }
+      else { y = fmaxf(pre, 0.f); dpre = (pre > 0.f) ? ds[j] * wx : 0.f; }
+      dw += ds[j] * y;
+      d2 += dpre;
+      if (accum) datt1[(long)j * A + x] += dpre; else datt1[(long)j * A + x] = dpre;
+    }
+    ds2row[x] = d2;
+    atomicAdd(dwv + x, dw);
+  }
+}
+
+// --------------------------------------------------------------------- context gate
+__global__ void ctx_gate_fwd_kernel(const float* __restrict__ s4, long ld_s4, const float* __restrict__ th,
+                                    long ld_th, float* __restrict__ zst, float* __restrict__ att_cap,
+                                    long ld_cap, int rows, int D) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    const float z = sigmoidf_(s4[i * ld_s4 + d]);
+    const float tsc = tanhf(s4[i * ld_s4 + D + d]);
+    const float ttc = tanhf(th[i * ld_th + d]);
+    float* o = zst + i * 3 * D;
+    o[d] = z; o[D + d] = tsc; o[2 * D + d] = ttc;
+    att_cap[i * ld_cap + d] = z * tsc + (1.f - z) * ttc;
+  }
+}
+__global__ void ctx_gate_bwd_kernel(const float* __restrict__ zst, const float* __restrict__ datt_cap,
+                                    long ld_dcap, float* __restrict__ dz_out, float* __restrict__ dtc_out,
+                                    long ld_ds2, float* __restrict__ dsc, int rows, int D) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    const float* o = zst + i * 3 * D;
+    const float z = o[d], tsc = o[D + d], ttc = o[2 * D + d];
+    const float g = datt_cap[i * ld_dcap + d];
+    dz_out[i * ld_ds2 + d] = g * (tsc - ttc) * z * (1.f - z);
+    dsc[x] = g * z * (1.f - tsc * tsc);
+    dtc_out[i * ld_ds2 + d] = g * (1.f - z) * (1.f - ttc * ttc);
+  }
+}
+
+// ------------------------------------------------------------------------ copy-LSTM
+__global__ void copy1_fwd_kernel(float* __restrict__ g2, const float* __restrict__ c2_prev,
+                                 float* __restrict__ cnew, int rows, int D) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    float* g = g2 + i * 4 * D;
+    const float gi = sigmoidf_(g[d]), gf = sigmoidf_(g[D + d]), gg = tanhf(g[2 * D + d]), go = sigmoidf_(g[3 * D + d]);
+    g[d] = gi; g[D + d] = gf; g[2 * D + d] = gg; g[3 * D + d] = go;
+    cnew[x] = gf * c2_prev[x] + gi * gg;
+  }
+}
+__global__ void copy2_fwd_kernel(const float* __restrict__ kpre, long ld_k, const float* __restrict__ g2,
+                                 const float* __restrict__ sel, const float* __restrict__ cnew,
+                                 float* __restrict__ kgate, float* __restrict__ c2, float* __restrict__ h2,
+                                 float* __restrict__ h2drop, int rows, int D, int train, uint64_t seed,
+                                 long drop_base) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    const float k = sigmoidf_(kpre[i * ld_k + d]);
+    const float c = k * sel[x] + (1.f - k) * cnew[x];
+    const float h = g2[i * 4 * D + 3 * D + d] * tanhf(c);
+    kgate[x] = k; c2[x] = c; h2[x] = h;
+    if (h2drop) {
+      float hd = h;
+      if (train) hd = drop_keep(seed, kSiteFc, (uint64_t)(drop_base + x)) ? h * 2.f : 0.f;
+      h2drop[x] = hd;
+    }
+  }
+}
+__global__ void copy2_bwd_kernel(const float* __restrict__ dh2_carry, const float* __restrict__ dh2drop_raw,
+                                 const float* __restrict__ dc2_carry, const float* __restrict__ g2,
+                                 const float* __restrict__ c2, const float* __restrict__ kgate,
+                                 const float* __restrict__ sel, const float* __restrict__ cnew,
+                                 float* __restrict__ dg2, float* __restrict__ dkpre, float* __restrict__ dsel,
+                                 float* __restrict__ dcnew, int rows, int D, int train, uint64_t seed,
+                                 long drop_base) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    float dfc = dh2drop_raw ? dh2drop_raw[x] : 0.f;
+    if (train && dh2drop_raw) dfc = drop_keep(seed, kSiteFc, (uint64_t)(drop_base + x)) ? dfc * 2.f : 0.f;
+    const float dh = dh2_carry[x] + dfc;
+    const float go = g2[i * 4 * D + 3 * D + d];
+    const float tc = tanhf(c2[x]);
+    dg2[i * 4 * D + 3 * D + d] = dh * tc * go * (1.f - go);
+    const float dc = dc2_carry[x] + dh * go * (1.f - tc * tc);
+    const float k = kgate[x];
+    dkpre[x] = dc * (sel[x] - cnew[x]) * k * (1.f - k);
+    dsel[x] = dc * k;
+    dcnew[x] = dc * (1.f - k);
+  }
+}
+__global__ void copy1_bwd_kernel(const float* __restrict__ dcnew, const float* __restrict__ g2,
+                                 const float* __restrict__ c2_prev, float* __restrict__ dg2,
+                                 float* __restrict__ dc2_carry, int rows, int D) {
+  const long total = (long)rows * D;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % D);
+    const long i = x / D;
+    const float* g = g2 + i * 4 * D;
+    const float gi = g[d], gf = g[D + d], gg = g[2 * D + d];
+    const float dc = dcnew[x];
+    float* dg = dg2 + i * 4 * D;
+    dg[d] = dc * gg * gi * (1.f - gi);
+    dg[D + d] = dc * c2_prev[x] * gf * (1.f - gf);
+    dg[2 * D + d] = dc * gi * (1.f - gg * gg);
+    dc2_carry[x] = dc * gf;
+  }
+}
+
+__global__ void dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, long n, int train,
+                                   uint64_t seed, uint32_t site, long base) {
+  for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < n; y += (long)gridDim.x * blockDim.x) {
+    float v = x[y];
+    if (train) v = drop_keep(seed, site, (uint64_t)(base + y)) ? v * 2.f : 0.f;
+    out[y] = v;
+  }
+}
+__global__ void sum_time_kernel(const float* __restrict__ x, float* __restrict__ out, int T, long n) {
+  for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < n; y += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += x[(long)t * n + y];
+    out[y] = s;
+  }
+}
+__global__ void keep_mask_kernel(float* __restrict__ out, long n, uint64_t seed, uint32_t site, long base) {
+  for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < n; y += (long)gridDim.x * blockDim.x)
+    out[y] = drop_keep(seed, site, (uint64_t)(base + y)) ? 1.f : 0.f;
+}
+
+#define LAUNCH_OK()                         \
+  SET_CHECK_CUDA(cudaGetLastError());       \
+  return SET_OK
+
+}  // namespace
+
+int embed_fwd(const int64_t* tokens, long tok_ld, long tok_os, const float* table, int V, float* out,
+              int n_outer, int n_inner, int D, int train, uint64_t seed, uint32_t site, long drop_row0,
+              long drop_os, long drop_is, cudaStream_t s) {
+  SET_REQUIRE(D % 4 == 0, "D % 4");
+  const long n = (long)n_outer * n_inner * (D / 4);
+  if (n == 0) return SET_OK;
+  embed_fwd_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(tokens, tok_ld, tok_os, table, V, out, n_outer,
+                                                                n_inner, D, train, seed, site, drop_row0, drop_os, drop_is);
+  LAUNCH_OK();
+}
+int embed_bwd(const int64_t* tokens, long tok_ld, long tok_os, const float* out, const float* dout,
+              float* table_grad, int V, int n_outer, int n_inner, int D, int train, const int* row_len,
+              cudaStream_t s) {
+  const long n = (long)n_outer * n_inner * D;
+  if (n == 0) return SET_OK;
+  embed_bwd_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(tokens, tok_ld, tok_os, out, dout, table_grad,
+                                                                V, n_outer, n_inner, D, train ? 2.f : 1.f, row_len);
+  LAUNCH_OK();
+}
+int region_mean(const float* feats, float* out, int B, int R, int F, cudaStream_t s) {
+  region_mean_kernel<<<blocks_for((long)B * F, kThreads), kThreads, 0, s>>>(feats, out, B, R, F);
+  LAUNCH_OK();
+}
+int region_count(const float* feats, int* nreg, int B, int R, int F, cudaStream_t s) {
+  region_count_kernel<<<B, kThreads, 0, s>>>(feats, nreg, R, F);
+  LAUNCH_OK();
+}
+int zero_pad_regions(float* fe, const int* nreg, int B, int R, int D, cudaStream_t s) {
+  zero_pad_regions_kernel<<<blocks_for((long)B * R * D, kThreads), kThreads, 0, s>>>(fe, nreg, B, R, D);
+  LAUNCH_OK();
+}
+int vis_dropout_fwd(const float* fe_pre, float* fe_t, int T, int B, int R, int D, uint64_t seed, cudaStream_t s) {
+  SET_REQUIRE(D % 4 == 0, "D % 4");
+  const long n = (long)B * R * D;
+  vis_dropout_fwd_kernel<<<blocks_for((long)T * n / 4, kThreads), kThreads, 0, s>>>(fe_pre, fe_t, T, n, seed);
+  LAUNCH_OK();
+}
+int vis_dropout_bwd(const float* fe_pre, const float* dfe_t, float* dfe_pre, const int* dec_len, int T, int B,
+                    int R, int D, uint64_t seed, cudaStream_t s) {
+  const long ps = (long)R * D;
+  vis_dropout_bwd_kernel<<<blocks_for((long)B * ps / 4, kThreads), kThreads, 0, s>>>(fe_pre, dfe_t, dfe_pre,
+                                                                                    dec_len, T, B, ps, seed);
+  LAUNCH_OK();
+}
+int relu_bwd_inplace(float* dx, const float* y, long n, cudaStream_t s) {
+  relu_bwd_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(dx, y, n);
+  LAUNCH_OK();
+}
+int tanh_bwd_inplace(float* dy, const float* y, long n, cudaStream_t s) {
+  tanh_bwd_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(dy, y, n);
+  LAUNCH_OK();
+}
+int lstm_fwd(const float* pre, long ld_pre, const float* c_prev, const float* h_prev, float* gates,
+             float* c_out, float* h_out, long ld_h, int rows, int D, const int64_t* len, int t, float* seq_h,
+             float* seq_m, long seq_ld, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  lstm_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
+      pre, ld_pre, c_prev, h_prev, gates, c_out, h_out, ld_h, rows, D, len, t, seq_h, seq_m, seq_ld);
+  LAUNCH_OK();
+}
+int lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dh, long ld_dh,
+             const float* dh_b, float* dc_carry, float* dgates, int rows, int D, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  lstm_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(gates, c_prev, c_cur, dh, ld_dh,
+                                                                            dh_b, dc_carry, dgates, rows, D);
+  LAUNCH_OK();
+}
+int enc_lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, float* dh_run, float* dc_run,
+                 const float* dseq_h, const float* dseq_m, long seq_ld, const float* dh_last,
+                 const int64_t* len, int t, float* dgates, int rows, int D, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  enc_lstm_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
+      gates, c_prev, c_cur, dh_run, dc_run, dseq_h, dseq_m, seq_ld, dh_last, len, t, dgates, rows, D);
+  LAUNCH_OK();
+}
+int enc_mask(const float* prev_m, float* mask, int B, int P, int D, cudaStream_t s) {
+  const long rows = (long)B * P;
+  enc_mask_kernel<<<(int)((rows * 32 + kThreads - 1) / kThreads), kThreads, 0, s>>>(prev_m, mask, rows, D);
+  LAUNCH_OK();
+}
+int attention_fwd(const AttnFwdArgs& a, cudaStream_t s) {
+  if (a.b <= 0) return SET_OK;
+  SET_REQUIRE(a.F % 4 == 0, "F % 4");
+  const int n = a.P > a.R ? a.P : a.R;
+  const size_t smem = sizeof(float) * (2 * a.A + n + 40);
+  SET_REQUIRE(smem <= 48 * 1024, "attention smem");
+  attention_fwd_kernel<<<dim3(a.b, 2), kThreads, smem, s>>>(a);
+  LAUNCH_OK();
+}
+int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
+  if (a.b <= 0) return SET_OK;
+  const int n = a.P > a.R ? a.P : a.R;
+  const size_t smem = sizeof(float) * (2 * a.A + 3 * n + 40);
+  SET_REQUIRE(smem <= 48 * 1024, "attention smem");
+  attention_bwd_kernel<<<dim3(a.b, 2), kThreads, smem, s>>>(a);
+  LAUNCH_OK();
+}
+int ctx_gate_fwd(const float* s4, long ld_s4, const float* th, long ld_th, float* zst, float* att_cap,
+                 long ld_cap, int rows, int D, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  ctx_gate_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(s4, ld_s4, th, ld_th, zst,
+                                                                                att_cap, ld_cap, rows, D);
+  LAUNCH_OK();
+}
+int ctx_gate_bwd(const float* zst, const float* datt_cap, long ld_dcap, float* dz_out, float* dtc_out,
+                 long ld_ds2, float* dsc, int rows, int D, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  ctx_gate_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(zst, datt_cap, ld_dcap, dz_out,
+                                                                                dtc_out, ld_ds2, dsc, rows, D);
+  LAUNCH_OK();
+}
+int copy1_fwd(float* g2, const float* c2_prev, float* cnew, int rows, int D, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  copy1_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(g2, c2_prev, cnew, rows, D);
+  LAUNCH_OK();
+}
+int copy2_fwd(const float* kpre, long ld_k, const float* g2, const float* sel, const float* cnew, float* kgate,
+              float* c2, float* h2, float* h2drop, int rows, int D, int train, uint64_t seed, long drop_base,
+              cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  copy2_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
+      kpre, ld_k, g2, sel, cnew, kgate, c2, h2, h2drop, rows, D, train, seed, drop_base);
+  LAUNCH_OK();
+}
+int copy2_bwd(const float* dh2_carry, const float* dh2drop_raw, const float* dc2_carry, const float* g2,
+              const float* c2, const float* kgate, const float* sel, const float* cnew, float* dg2,
+              float* dkpre, float* dsel, float* dcnew, int rows, int D, int train, uint64_t seed, long drop_base,
+              cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  copy2_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
+      dh2_carry, dh2drop_raw, dc2_carry, g2, c2, kgate, sel, cnew, dg2, dkpre, dsel, dcnew, rows, D, train, seed,
+      drop_base);
+  LAUNCH_OK();
+}
+int copy1_bwd(const float* dcnew, const float* g2, const float* c2_prev, float* dg2, float* dc2_carry, int rows,
+              int D, cudaStream_t s) {
+  if (rows <= 0) return SET_OK;
+  copy1_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(dcnew, g2, c2_prev, dg2, dc2_carry,
+                                                                             rows, D);
+  LAUNCH_OK();
+}
+int dropout_fwd(const float* x, float* out, int rows, int D, int train, uint64_t seed, uint32_t site,
+                long drop_base, cudaStream_t s) {
+  const long n = (long)rows * D;
+  if (n <= 0) return SET_OK;
+  dropout_fwd_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(x, out, n, train, seed, site, drop_base);
+  LAUNCH_OK();
+}
+int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s) {
+  sum_time_kernel<<<blocks_for(BN, kThreads), kThreads, 0, s>>>(x, out, T, BN);
+  LAUNCH_OK();
+}
+int dropout_keep_mask(float* out, long n, uint64_t seed, uint32_t site, long base, cudaStream_t s) {
+  if (n <= 0) return SET_OK;
+  keep_mask_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(out, n, seed, site, base);
+  LAUNCH_OK();
+}
+
+}  // namespace set

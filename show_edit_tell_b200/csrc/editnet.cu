@@ -1,0 +1,947 @@
+// Host orchestration + C ABI of the EditNet path: caption encoder, hoisted projections,
+// the per-step kernel chain, batched vocabulary projection, and the full reverse pass.
+// Reference: DecoderC.forward editnet.py:479-548, editnet_rl.py:485-549,
+// adaptive_features/editnet_adaptive.py:489-562 and the cells they call (editnet.py:210-447).
+//
+// Data layout in HBM (fp32).  Per-sequence tensors are batch-major like the reference's
+// ([B][P][D] encoder outputs, [B][R][F] features); everything the recurrence saves is
+// time-major ([T][B][.]) so a step's rows are contiguous and the time-batched contractions
+// (vocabulary projection, every dW, the hoisted word/feature projections) see one dense
+// [T*B, K] operand.  The concatenations of the reference are never materialised: X2[t] =
+// [h1 | att_cap | att_img] is written in place by the producing kernels, and GEMM
+// K-segments read [h2 ; h1] or column blocks of weight_ih where they lie.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/set_b200.h"
+#include "cells.cuh"
+#include "gemm.cuh"
+
+namespace set {
+
+namespace {
+
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0;
+  struct Entry { std::string name; size_t off, bytes; };
+  std::vector<Entry> entries;
+  template <typename T>
+  T* take(const char* name, size_t n) {
+    const size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    entries.push_back({name, off, n * sizeof(T)});
+    off += bytes;
+    return p;
+  }
+};
+
+struct Ws {
+  // ---- zeroed at the start of forward (region A)
+  float *emb_prev, *enc_xg, *enc_gates, *enc_h, *enc_c, *prev_h, *prev_m, *mask, *fh, *att1c;
+  float *image_mean, *fe_pre, *att1, *fe_t, *pre1s, *emb_all, *pre1, *gw, *tw;
+  float *gates1, *c1, *X2, *s2, *g2, *alpha_c, *ctx_c, *sel, *alpha_v, *zst, *cnew, *kgate, *c2, *h2, *h2drop;
+  float *logits, *lse, *scratch4d, *s4, *ones;
+  int *sel_idx, *nreg, *dec_len, *unfinished, *unf_count;
+  int64_t *it, *tok_raw;
+  // ---- zeroed at the start of backward (region B)
+  float *dG1, *dS2, *dG2, *dsc, *dK, *dh2raw, *datt1, *datt1c, *dprev_h, *dprev_m, *dfh, *dfe_pre, *dfe_t;
+  float *demb_all, *demb_prev, *denc_g, *dh_last, *dh_run, *dc_run, *sumG1;
+  float *dh2c, *dc2c, *dh1c, *dc1c, *dX2, *dctx, *dsel, *dcnew;
+  size_t regionA_end = 0, regionB_begin = 0, total = 0;
+};
+
+struct Ctx {
+  SetDims d;
+  SetSeqShape s;
+  const SetEditNetParams* w;
+  Ws ws;
+  cudaStream_t st;
+  uint64_t seed;
+  int LS2, LX2;
+};
+
+void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
+  const size_t B = s.B, P = s.P, T = s.T, R = s.R, D = d.D, A = d.A, F = d.F, V = d.V;
+  const size_t Tv = s.train ? T : 1;  // per-step visual tensors exist only with dropout
+  w.emb_prev = ar.take<float>("emb_prev", P * B * D);
+  w.enc_xg = ar.take<float>("enc_xg", P * B * 4 * D);
+  w.enc_gates = ar.take<float>("enc_gates", P * B * 4 * D);
+  w.enc_h = ar.take<float>("enc_h", (P + 1) * B * D);
+  w.enc_c = ar.take<float>("enc_c", (P + 1) * B * D);
+  w.prev_h = ar.take<float>("prev_h", B * P * D);
+  w.prev_m = ar.take<float>("prev_m", B * P * D);
+  w.mask = ar.take<float>("mask", B * P);
+  w.fh = ar.take<float>("final_hidden", B * D);
+  w.att1c = ar.take<float>("att1c", B * P * A);
+  w.image_mean = ar.take<float>("image_mean", B * F);
+  w.fe_pre = ar.take<float>("fe_pre", B * R * D);
+  w.att1 = ar.take<float>("att1", Tv * B * R * A);
+  w.fe_t = ar.take<float>("fe_t", s.train ? T * B * R * D : 1);
+  w.pre1s = ar.take<float>("pre1s", B * 4 * D);
+  w.emb_all = ar.take<float>("emb_all", T * B * D);
+  w.pre1 = ar.take<float>("pre1", T * B * 4 * D);
+  w.gw = ar.take<float>("gw", T * B * D);
+  w.tw = ar.take<float>("tw", T * B * D);
+  w.gates1 = ar.take<float>("gates1", T * B * 4 * D);
+  w.c1 = ar.take<float>("c1", (T + 1) * B * D);
+  w.X2 = ar.take<float>("X2", T * B * (2 * D + F));
+  w.s2 = ar.take<float>("s2", T * B * (2 * A + 2 * D));
+  w.g2 = ar.take<float>("g2", T * B * 4 * D);
+  w.alpha_c = ar.take<float>("alpha_c", T * B * P);
+  w.ctx_c = ar.take<float>("ctx_c", T * B * D);
+  w.sel = ar.take<float>("sel", T * B * D);
+  w.alpha_v = ar.take<float>("alpha_v", T * B * R);
+  w.zst = ar.take<float>("zst", T * B * 3 * D);
+  w.cnew = ar.take<float>("cnew", T * B * D);
+  w.kgate = ar.take<float>("kgate", T * B * D);
+  w.c2 = ar.take<float>("c2", (T + 1) * B * D);
+  w.h2 = ar.take<float>("h2", (T + 1) * B * D);
+  w.h2drop = ar.take<float>("h2drop", T * B * D);
+  w.logits = ar.take<float>("logits", Tv * B * V);   // rollouts only use it; XE writes to `predictions`
+  w.lse = ar.take<float>("lse", T * B);
+  w.scratch4d = ar.take<float>("scratch4d", B * 4 * D);
+  w.s4 = ar.take<float>("s4", B * 3 * D);
+  w.ones = ar.take<float>("ones", T * B);
+  w.sel_idx = ar.take<int>("sel_idx", T * B);
+  w.nreg = ar.take<int>("nreg", B);
+  w.dec_len = ar.take<int>("dec_len", B);
+  w.unfinished = ar.take<int>("unfinished", B);
+  w.unf_count = ar.take<int>("unf_count", T + 2);
+  w.it = ar.take<int64_t>("it", (T + 1) * B);
+  w.tok_raw = ar.take<int64_t>("tok_raw", T * B);
+  w.regionA_end = ar.off;
+  w.regionB_begin = ar.off;
+  w.dG1 = ar.take<float>("dG1", T * B * 4 * D);
+  w.dS2 = ar.take<float>("dS2", T * B * (2 * A + 2 * D));
+  w.dG2 = ar.take<float>("dG2", T * B * 4 * D);
+  w.dsc = ar.take<float>("dsc", T * B * D);
+  w.dK = ar.take<float>("dK", T * B * D);
+  w.dh2raw = ar.take<float>("dh2raw", T * B * D);
+  w.datt1 = ar.take<float>("datt1", Tv * B * R * A);
+  w.datt1c = ar.take<float>("datt1c", B * P * A);
+  w.dprev_h = ar.take<float>("dprev_h", B * P * D);
+  w.dprev_m = ar.take<float>("dprev_m", B * P * D);
+  w.dfh = ar.take<float>("dfh", B * D);
+  w.dfe_pre = ar.take<float>("dfe_pre", B * R * D);
+  w.dfe_t = ar.take<float>("dfe_t", s.train ? T * B * R * D : 1);
+  w.demb_all = ar.take<float>("demb_all", T * B * D);
+  w.demb_prev = ar.take<float>("demb_prev", P * B * D);
+  w.denc_g = ar.take<float>("denc_g", P * B * 4 * D);
+  w.dh_last = ar.take<float>("dh_last", B * D);
+  w.dh_run = ar.take<float>("dh_run", B * D);
+  w.dc_run = ar.take<float>("dc_run", B * D);
+  w.sumG1 = ar.take<float>("sumG1", B * 4 * D);
+  w.dh2c = ar.take<float>("dh2c", B * D);
+  w.dc2c = ar.take<float>("dc2c", B * D);
+  w.dh1c = ar.take<float>("dh1c", B * D);
+  w.dc1c = ar.take<float>("dc1c", B * D);
+  w.dX2 = ar.take<float>("dX2", B * (2 * D + F));
+  w.dctx = ar.take<float>("dctx", B * D);
+  w.dsel = ar.take<float>("dsel", B * D);
+  w.dcnew = ar.take<float>("dcnew", B * D);
+  w.total = ar.off;
+}
+
+int check_args(const SetDims* d, const SetSeqShape* s) {
+  SET_REQUIRE(d && s, "null dims/shape");
+  SET_REQUIRE(d->D > 0 && d->D % 4 == 0 && d->A > 0 && d->A % 4 == 0 && d->F > 0 && d->F % 4 == 0 && d->V > 1,
+              "D, A, F must be positive multiples of 4");
+  SET_REQUIRE(s->B > 0 && s->R > 0 && s->R <= 1024 && s->Wp > 0 && s->P > 0 && s->P <= s->Wp && s->T > 0,
+              "bad sequence shape");
+  SET_REQUIRE(d->A <= 4096, "attention_dim too large for the attention kernel's shared memory");
+  return SET_OK;
+}
+
+int make_ctx(Ctx& c, const SetDims* d, const SetSeqShape* s, const SetEditNetParams* w, void* workspace,
+             size_t workspace_bytes, uint64_t seed, void* stream) {
+  SET_PROPAGATE(check_args(d, s));
+  SET_REQUIRE(w != nullptr && workspace != nullptr, "null params/workspace");
+  SET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  c.d = *d; c.s = *s; c.w = w; c.seed = seed;
+  c.st = reinterpret_cast<cudaStream_t>(stream);
+  Arena ar;
+  ar.base = reinterpret_cast<char*>(workspace);
+  layout(*d, *s, ar, c.ws);
+  if (c.ws.total > workspace_bytes) {
+    set_record_error("workspace too small: see set_editnet_workspace_bytes()");
+    return SET_ERR_WORKSPACE;
+  }
+  c.LS2 = 2 * d->A + 2 * d->D;
+  c.LX2 = 2 * d->D + d->F;
+  return SET_OK;
+}
+
+__global__ void fill_kernel(float* p, long n, float v) {
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) p[x] = v;
+}
+__global__ void fill_i64_kernel(int64_t* p, long n, int64_t v) {
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) p[x] = v;
+}
+
+// --------------------------------------------------------------------- shared prologue
+// caption encoder (editnet.py:319-348), image mean (:503), hoisted time-invariant projections
+int prepare_common(Ctx& c, const float* feats, const float* image_mean_in, const int64_t* prev,
+                   const int64_t* prev_len) {
+  const int B = c.s.B, P = c.s.P, T = c.s.T, R = c.s.R, D = c.d.D, A = c.d.A, F = c.d.F;
+  const SetEditNetParams& w = *c.w;
+  Ws& s = c.ws;
+  cudaStream_t st = c.st;
+  SET_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(s.emb_prev), 0, s.regionA_end, st));
+  fill_kernel<<<8, 256, 0, st>>>(s.ones, (long)T * B, 1.0f);
+  SET_CHECK_CUDA(cudaGetLastError());
+  // --- previous-caption encoder
+  SET_PROPAGATE(embed_fwd(prev, c.s.Wp, 1, w.embed, c.d.V, s.emb_prev, P, B, D, c.s.train, c.seed, kSiteEnc, 0, 1,
+                          c.s.Wp, st));
+  {
+    GemmProblem p = gemm_problem(P * B, 4 * D, s.enc_xg, 4 * D);
+    gemm_add_seg(p, s.emb_prev, D, w.enc_x2h_w, D, D);
+    p.bias = w.enc_x2h_b; p.bias2 = w.enc_h2h_b;
+    SET_PROPAGATE(gemm(kNT, p, st));
+  }
+  for (int t = 0; t < P; ++t) {
+    GemmProblem p = gemm_problem(B, 4 * D, s.scratch4d, 4 * D);
+    if (t > 0) gemm_add_seg(p, s.enc_h + (size_t)t * B * D, D, w.enc_h2h_w, D, D);
+    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D;
+    SET_PROPAGATE(gemm(kNT, p, st));
+    SET_PROPAGATE(lstm_fwd(s.scratch4d, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
+                           s.enc_gates + (size_t)t * B * 4 * D, s.enc_c + (size_t)(t + 1) * B * D,
+                           s.enc_h + (size_t)(t + 1) * B * D, D, B, D, prev_len, t, s.prev_h, s.prev_m,
+                           (long)P * D, st));
+  }
+  SET_PROPAGATE(enc_mask(s.prev_m, s.mask, B, P, D, st));
+  {
+    GemmProblem p[2];
+    p[0] = gemm_problem(B, D, s.fh, D);   // final_hidden = tanh(affine_hn(h_last)), editnet.py:341
+    gemm_add_seg(p[0], s.enc_h + (size_t)P * B * D, D, w.enc_aff_w, D, D);
+    p[0].bias = w.enc_aff_b; p[0].act = 2;
+    SET_PROPAGATE(gemm(kNT, p[0], st));
+    p[1] = gemm_problem(B * P, A, s.att1c, A);  // cap_features_att(prev_h), editnet.py:370 (time-invariant)
+    gemm_add_seg(p[1], s.prev_h, D, w.ca_feat_w, D, D);
+    p[1].bias = w.ca_feat_b;
+    SET_PROPAGATE(gemm(kNT, p[1], st));
+  }
+  // --- image side
+  if (c.s.adaptive) {
+    SET_REQUIRE(image_mean_in != nullptr, "adaptive needs image_mean");
+    SET_CHECK_CUDA(cudaMemcpyAsync(s.image_mean, image_mean_in, sizeof(float) * B * F, cudaMemcpyDeviceToDevice, st));
+    SET_PROPAGATE(region_count(feats, s.nreg, B, R, F, st));
+  } else {
+    SET_PROPAGATE(region_mean(feats, s.image_mean, B, R, F, st));
+  }
+  {
+    GemmProblem p = gemm_problem(B * R, D, s.fe_pre, D);  // relu(att_embed.0(feats)), editnet.py:430-431,441
+    gemm_add_seg(p, feats, F, w.va_emb_w, F, F);
+    p.bias = w.va_emb_b; p.act = 1;
+    SET_PROPAGATE(gemm(kNT, p, st));
+  }
+  if (c.s.adaptive) SET_PROPAGATE(zero_pad_regions(s.fe_pre, s.nreg, B, R, D, st));
+  if (c.s.train) {
+    // dropout is redrawn every step (editnet.py:432), so features_att is re-projected per step --
+    // but it does not depend on the recurrence: all T steps go through one time-batched GEMM.
+    SET_PROPAGATE(vis_dropout_fwd(s.fe_pre, s.fe_t, T, B, R, D, c.seed, st));
+    GemmProblem p = gemm_problem(T * B * R, A, s.att1, A);
+    gemm_add_seg(p, s.fe_t, D, w.va_feat_w, D, D);
+    p.bias = w.va_feat_b;
+    SET_PROPAGATE(gemm(kNT, p, st));
+  } else {
+    GemmProblem p = gemm_problem(B * R, A, s.att1, A);
+    gemm_add_seg(p, s.fe_pre, D, w.va_feat_w, D, D);
+    p.bias = w.va_feat_b;
+    SET_PROPAGATE(gemm(kNT, p, st));
+  }
+  {
+    // attention-LSTM input columns that do not change over time: final_hidden and image_mean
+    GemmProblem p = gemm_problem(B, 4 * D, s.pre1s, 4 * D);
+    gemm_add_seg(p, s.fh, D, w.al_wih + D, 3 * D + F, D);
+    gemm_add_seg(p, s.image_mean, F, w.al_wih + 3 * D, 3 * D + F, F);
+    p.bias = w.al_bih; p.bias2 = w.al_bhh;
+    SET_PROPAGATE(gemm(kNT, p, st));
+  }
+  return SET_OK;
+}
+
+// word-dependent projections for rows [t0, t0+nt) x B of emb_all (hoisted for teacher forcing,
+// per step for rollouts)
+int project_words(Ctx& c, int t0, int nt) {
+  const int B = c.s.B, D = c.d.D, F = c.d.F;
+  const SetEditNetParams& w = *c.w;
+  Ws& s = c.ws;
+  const size_t r0 = (size_t)t0 * B;
+  GemmProblem p[3];
+  p[0] = gemm_problem(nt * B, 4 * D, s.pre1 + r0 * 4 * D, 4 * D);
+  gemm_add_seg(p[0], s.emb_all + r0 * D, D, w.al_wih, 3 * D + F, D);
+  p[0].add = s.pre1s; p[0].ldadd = 4 * D; p[0].add_mod = B;
+  p[1] = gemm_problem(nt * B, D, s.gw + r0 * D, D);
+  gemm_add_seg(p[1], s.emb_all + r0 * D, D, w.ca_gate_w, 3 * D, D);
+  p[1].bias = w.ca_gate_b;
+  p[2] = gemm_problem(nt * B, D, s.tw + r0 * D, D);
+  gemm_add_seg(p[2], s.emb_all + r0 * D, D, w.ca_tc_w, 2 * D, D);
+  p[2].bias = w.ca_tc_b;
+  return gemm_group(kNT, p, 3, c.st);
+}
+
+// one decode step on rows [0,b): SURVEY.md Appendix A steps 2-7 (editnet.py:527-543)
+int step_forward(Ctx& c, const float* feats, int t, int b) {
+  const int B = c.s.B, P = c.s.P, R = c.s.R, D = c.d.D, A = c.d.A, F = c.d.F;
+  const int LS2 = c.LS2, LX2 = c.LX2;
+  const SetEditNetParams& w = *c.w;
+  Ws& s = c.ws;
+  cudaStream_t st = c.st;
+  float* X2t = s.X2 + (size_t)t * B * LX2;
+  float* s2t = s.s2 + (size_t)t * B * LS2;
+  float* g2t = s.g2 + (size_t)t * B * 4 * D;
+  const float* h2prev = s.h2 + (size_t)t * B * D;
+  {  // attention-LSTM recurrent part: W_ih[:,2D:3D] h2 + W_hh h1 + hoisted terms (editnet.py:532)
+    GemmProblem p = gemm_problem(b, 4 * D, s.scratch4d, 4 * D);
+    if (t > 0) {
+      gemm_add_seg(p, h2prev, D, w.al_wih + 2 * D, 3 * D + F, D);
+      gemm_add_seg(p, s.X2 + (size_t)(t - 1) * B * LX2, LX2, w.al_whh, D, D);
+    }
+    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D;
+    SET_PROPAGATE(gemm(kNT, p, st));
+    SET_PROPAGATE(lstm_fwd(s.scratch4d, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
+                           s.c1 + (size_t)(t + 1) * B * D, X2t, LX2, b, D, nullptr, 0, nullptr, nullptr, 0, st));
+  }
+  {  // everything that consumes h1 in one grouped launch
+    GemmProblem p[5];
+    p[0] = gemm_problem(b, A, s2t, LS2);                     // cap_decoder_att(h1), :371
+    gemm_add_seg(p[0], X2t, LX2, w.ca_dec_w, D, D); p[0].bias = w.ca_dec_b;
+    p[1] = gemm_problem(b, A, s2t + A, LS2);                 // decoder_att(h1), :443
+    gemm_add_seg(p[1], X2t, LX2, w.va_dec_w, D, D); p[1].bias = w.va_dec_b;
+    p[2] = gemm_problem(b, D, s2t + 2 * A, LS2);             // context_gate[:, D:2D] h1 + word part, :378
+    gemm_add_seg(p[2], X2t, LX2, w.ca_gate_w + D, 3 * D, D);
+    p[2].add = s.gw + (size_t)t * B * D; p[2].ldadd = D;
+    p[3] = gemm_problem(b, D, s2t + 2 * A + D, LS2);         // tc_affine[:, D:2D] h1 + word part, :379-380
+    gemm_add_seg(p[3], X2t, LX2, w.ca_tc_w + D, 2 * D, D);
+    p[3].add = s.tw + (size_t)t * B * D; p[3].ldadd = D;
+    p[4] = gemm_problem(b, 4 * D, g2t, 4 * D);               // copy_lstm: x2h[:, 0:D] h1 + h2h h2, :272
+    gemm_add_seg(p[4], X2t, LX2, w.cl_x2h_w, LX2, D);
+    if (t > 0) gemm_add_seg(p[4], h2prev, D, w.cl_h2h_w, D, D);
+    p[4].bias = w.cl_x2h_b; p[4].bias2 = w.cl_h2h_b;
+    SET_PROPAGATE(gemm_group(kNT, p, 5, st));
+  }
+  {
+    AttnFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.b = b; a.P = P; a.R = R; a.D = D; a.A = A; a.F = F;
+    a.att1c = s.att1c; a.s2 = s2t; a.ld_s2 = LS2; a.cap_w = w.ca_full_w; a.cap_b = w.ca_full_b;
+    a.mask = s.mask; a.prev_h = s.prev_h; a.prev_m = s.prev_m;
+    a.alpha_c = s.alpha_c + (size_t)t * B * P; a.ctx = s.ctx_c + (size_t)t * B * D;
+    a.sel = s.sel + (size_t)t * B * D; a.sel_idx = s.sel_idx + (size_t)t * B;
+    a.att1v = c.s.train ? s.att1 + (size_t)t * B * R * A : s.att1;
+    a.vis_w = w.va_full_w; a.vis_b = w.va_full_b; a.feats = feats;
+    a.nreg = c.s.adaptive ? s.nreg : nullptr;
+    a.alpha_v = s.alpha_v + (size_t)t * B * R; a.att_img = X2t + 2 * D; a.ld_img = LX2;
+    SET_PROPAGATE(attention_fwd(a, st));
+  }
+  {
+    const float* ctx = s.ctx_c + (size_t)t * B * D;
+    GemmProblem p[3];
+    p[0] = gemm_problem(b, D, s.s4, 3 * D);                  // context_gate[:, 2D:3D] ctx (+ h1/word parts)
+    gemm_add_seg(p[0], ctx, D, w.ca_gate_w + 2 * D, 3 * D, D);
+    p[0].add = s2t + 2 * A; p[0].ldadd = LS2;
+    p[1] = gemm_problem(b, D, s.s4 + D, 3 * D);              // sc_affine(ctx), :380
+    gemm_add_seg(p[1], ctx, D, w.ca_sc_w, D, D); p[1].bias = w.ca_sc_b;
+    p[2] = gemm_problem(b, D, s.s4 + 2 * D, 3 * D);          // gate_cmem(sel) (+ both copy-gate biases), :281
+    gemm_add_seg(p[2], s.sel + (size_t)t * B * D, D, w.cl_gcm_w, D, D);
+    p[2].bias = w.cl_gcm_b; p[2].bias2 = w.cl_gcn_b;
+    SET_PROPAGATE(gemm_group(kNT, p, 3, st));
+    SET_PROPAGATE(ctx_gate_fwd(s.s4, 3 * D, s2t + 2 * A + D, LS2, s.zst + (size_t)t * B * 3 * D, X2t + D, LX2, b, D, st));
+  }
+  {
+    GemmProblem p = gemm_problem(b, 4 * D, g2t, 4 * D);      // x2h[:, D:] [att_cap | att_img], :272
+    gemm_add_seg(p, X2t + D, LX2, w.cl_x2h_w + D, LX2, D + F);
+    p.beta = 1;
+    SET_PROPAGATE(gemm(kNT, p, st));
+    SET_PROPAGATE(copy1_fwd(g2t, s.c2 + (size_t)t * B * D, s.cnew + (size_t)t * B * D, b, D, st));
+  }
+  {
+    GemmProblem p = gemm_problem(b, D, s.s4 + 2 * D, 3 * D);  // gate_cnew(c_new), :281
+    gemm_add_seg(p, s.cnew + (size_t)t * B * D, D, w.cl_gcn_w, D, D);
+    p.beta = 1;
+    SET_PROPAGATE(gemm(kNT, p, st));
+    SET_PROPAGATE(copy2_fwd(s.s4 + 2 * D, 3 * D, g2t, s.sel + (size_t)t * B * D, s.cnew + (size_t)t * B * D,
+                            s.kgate + (size_t)t * B * D, s.c2 + (size_t)(t + 1) * B * D,
+                            s.h2 + (size_t)(t + 1) * B * D, s.h2drop + (size_t)t * B * D, b, D, c.s.train, c.seed,
+                            (long)t * B * D, st));
+  }
+  return SET_OK;
+}
+
+// ------------------------------------------------------------------------ reverse pass
+struct DLogits {
+  const float* p; long ld; int inner; long ld_inner; const int* row_len;  // rows are time-major m = t*B + i
+};
+
+int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const int64_t* caps_tok, long tok_ld,
+                  long tok_os, const int64_t* prev, const int64_t* prev_len, const int* bt_host, DLogits dl) {
+  const int B = c.s.B, P = c.s.P, T = c.s.T, R = c.s.R, D = c.d.D, A = c.d.A, F = c.d.F, V = c.d.V;
+  const int LS2 = c.LS2, LX2 = c.LX2;
+  const SetEditNetParams& w = *c.w;
+  Ws& s = c.ws;
+  cudaStream_t st = c.st;
+  const int TB = T * B;
+  SET_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(s.emb_prev) + s.regionB_begin, 0,
+                                 s.total - s.regionB_begin, st));
+  {  // d(dropout(h2)) for every step at once: dlogits @ fc.weight
+    GemmProblem p = gemm_problem(TB, D, s.dh2raw, D);
+    gemm_add_seg(p, dl.p, dl.ld, w.fc_w, D, V);
+    p.a_inner = dl.inner; p.a_ld_inner = dl.ld_inner; p.a_row_len = dl.row_len; p.a_valid_inner = B;
+    SET_PROPAGATE(gemm(kNN, p, st));
+  }
+  for (int t = T - 1; t >= 0; --t) {
+    const int b = bt_host[t];
+    if (b <= 0) continue;
+    const size_t tb = (size_t)t * B;
+    float* dG1t = s.dG1 + tb * 4 * D;
+    float* dG2t = s.dG2 + tb * 4 * D;
+    float* dS2t = s.dS2 + tb * LS2;
+    float* dKt = s.dK + tb * D;
+    const float* g2t = s.g2 + tb * 4 * D;
+    SET_PROPAGATE(copy2_bwd(s.dh2c, s.dh2raw + tb * D, s.dc2c, g2t, s.c2 + (tb + B) * D, s.kgate + tb * D,
+                            s.sel + tb * D, s.cnew + tb * D, dG2t, dKt, s.dsel, s.dcnew, b, D, c.s.train, c.seed,
+                            (long)tb * D, st));
+    {
+      GemmProblem p[2];
+      p[0] = gemm_problem(b, D, s.dcnew, D); gemm_add_seg(p[0], dKt, D, w.cl_gcn_w, D, D); p[0].beta = 1;
+      p[1] = gemm_problem(b, D, s.dsel, D); gemm_add_seg(p[1], dKt, D, w.cl_gcm_w, D, D); p[1].beta = 1;
+      SET_PROPAGATE(gemm_group(kNN, p, 2, st));
+    }
+    SET_PROPAGATE(copy1_bwd(s.dcnew, g2t, s.c2 + tb * D, dG2t, s.dc2c, b, D, st));
+    {
+      GemmProblem p = gemm_problem(b, LX2, s.dX2, LX2);      // d[h1 | att_cap | att_img]
+      gemm_add_seg(p, dG2t, 4 * D, w.cl_x2h_w, LX2, 4 * D);
+      SET_PROPAGATE(gemm(kNN, p, st));
+    }
+    SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, s.dX2 + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
+                               s.dsc + tb * D, b, D, st));
+    {
+      GemmProblem p = gemm_problem(b, D, s.dctx, D);
+      gemm_add_seg(p, dS2t + 2 * A, LS2, w.ca_gate_w + 2 * D, 3 * D, D);
+      gemm_add_seg(p, s.dsc + tb * D, D, w.ca_sc_w, D, D);
+      SET_PROPAGATE(gemm(kNN, p, st));
+    }
+    {
+      AttnBwdArgs a;
+      memset(&a, 0, sizeof(a));
+      a.b = b; a.P = P; a.R = R; a.D = D; a.A = A; a.F = F;
+      a.att1c = s.att1c; a.s2 = s.s2 + tb * LS2; a.ld_s2 = LS2; a.cap_w = w.ca_full_w; a.mask = s.mask;
+      a.prev_h = s.prev_h; a.prev_m = s.prev_m; a.alpha_c = s.alpha_c + tb * P; a.sel_idx = s.sel_idx + tb;
+      a.dctx = s.dctx; a.dsel = s.dsel; a.dprev_h = s.dprev_h; a.dprev_m = s.dprev_m; a.datt1c = s.datt1c;
+      a.ds2 = dS2t; a.ld_ds2 = LS2; a.dcap_w = g.ca_full_w; a.dcap_b = g.ca_full_b;
+      a.att1v = c.s.train ? s.att1 + tb * R * A : s.att1; a.vis_w = w.va_full_w; a.feats = feats;
+      a.nreg = c.s.adaptive ? s.nreg : nullptr; a.alpha_v = s.alpha_v + tb * R;
+      a.datt_img = s.dX2 + 2 * D; a.ld_dimg = LX2;
+      a.datt1v = c.s.train ? s.datt1 + tb * R * A : s.datt1; a.datt1v_accum = c.s.train ? 0 : 1;
+      a.dvis_w = g.va_full_w; a.dvis_b = g.va_full_b;
+      SET_PROPAGATE(attention_bwd(a, st));
+    }
+    {
+      GemmProblem p = gemm_problem(b, D, s.dX2, LX2);        // dh1 += every consumer of h1
+      gemm_add_seg(p, dS2t, LS2, w.ca_dec_w, D, A);
+      gemm_add_seg(p, dS2t + A, LS2, w.va_dec_w, D, A);
+      gemm_add_seg(p, dS2t + 2 * A, LS2, w.ca_gate_w + D, 3 * D, D);
+      gemm_add_seg(p, dS2t + 2 * A + D, LS2, w.ca_tc_w + D, 2 * D, D);
+      p.beta = 1;
+      SET_PROPAGATE(gemm(kNN, p, st));
+    }
+    SET_PROPAGATE(lstm_bwd(s.gates1 + tb * 4 * D, s.c1 + tb * D, s.c1 + (tb + B) * D, s.dX2, LX2, s.dh1c, s.dc1c,
+                           dG1t, b, D, st));
+    if (t > 0) {
+      GemmProblem p[2];
+      p[0] = gemm_problem(b, D, s.dh1c, D); gemm_add_seg(p[0], dG1t, 4 * D, w.al_whh, D, 4 * D);
+      p[1] = gemm_problem(b, D, s.dh2c, D);
+      gemm_add_seg(p[1], dG1t, 4 * D, w.al_wih + 2 * D, 3 * D + F, 4 * D);
+      gemm_add_seg(p[1], dG2t, 4 * D, w.cl_h2h_w, D, 4 * D);
+      SET_PROPAGATE(gemm_group(kNN, p, 2, st));
+    }
+  }
+  // ---- time-batched tail: input gradients
+  SET_PROPAGATE(sum_time(s.dG1, s.sumG1, T, (long)B * 4 * D, st));
+  {
+    GemmProblem p[2];
+    p[0] = gemm_problem(B, D, s.dfh, D);                      // d final_hidden
+    gemm_add_seg(p[0], s.sumG1, 4 * D, w.al_wih + D, 3 * D + F, 4 * D);
+    p[1] = gemm_problem(TB, D, s.demb_all, D);                // d embeddings (three consumers)
+    gemm_add_seg(p[1], s.dG1, 4 * D, w.al_wih, 3 * D + F, 4 * D);
+    gemm_add_seg(p[1], s.dS2 + 2 * A, LS2, w.ca_gate_w, 3 * D, D);
+    gemm_add_seg(p[1], s.dS2 + 2 * A + D, LS2, w.ca_tc_w, 2 * D, D);
+    SET_PROPAGATE(gemm_group(kNN, p, 2, st));
+  }
+  SET_PROPAGATE(embed_bwd(caps_tok, tok_ld, tok_os, s.emb_all, s.demb_all, g.embed, V, T, B, D, c.s.train,
+                          dl.row_len, st));
+  // ---- time-batched tail: weight gradients (dY^T X over all T*B rows; undecoded rows are zero)
+  auto TN = [&](float* C, long ldc, int M, int N, const float* dY, long ldy, const float* X, long ldx, int K) {
+    GemmProblem p = gemm_problem(M, N, C, ldc);
+    gemm_add_seg(p, dY, ldy, X, ldx, K);
+    p.beta = 1;
+    return p;
+  };
+  {
+    GemmProblem p[8];
+    int n = 0;
+    if (T > 1) p[n++] = TN(g.al_whh, D, 4 * D, D, s.dG1 + (size_t)B * 4 * D, 4 * D, s.X2, LX2, (T - 1) * B);
+    p[n++] = TN(g.al_wih, 3 * D + F, 4 * D, D, s.dG1, 4 * D, s.emb_all, D, TB);
+    p[n++] = TN(g.al_wih + D, 3 * D + F, 4 * D, D, s.sumG1, 4 * D, s.fh, D, B);
+    p[n++] = TN(g.al_wih + 2 * D, 3 * D + F, 4 * D, D, s.dG1, 4 * D, s.h2, D, TB);
+    p[n++] = TN(g.al_wih + 3 * D, 3 * D + F, 4 * D, F, s.sumG1, 4 * D, s.image_mean, F, B);
+    p[n++] = TN(g.cl_x2h_w, LX2, 4 * D, LX2, s.dG2, 4 * D, s.X2, LX2, TB);
+    p[n++] = TN(g.cl_h2h_w, D, 4 * D, D, s.dG2, 4 * D, s.h2, D, TB);
+    SET_PROPAGATE(gemm_group(kTN, p, n, st));
+  }
+  {
+    GemmProblem p[8];
+    int n = 0;
+    p[n++] = TN(g.ca_dec_w, D, A, D, s.dS2, LS2, s.X2, LX2, TB);
+    p[n++] = TN(g.va_dec_w, D, A, D, s.dS2 + A, LS2, s.X2, LX2, TB);
+    p[n++] = TN(g.ca_gate_w, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.emb_all, D, TB);
+    p[n++] = TN(g.ca_gate_w + D, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.X2, LX2, TB);
+    p[n++] = TN(g.ca_gate_w + 2 * D, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.ctx_c, D, TB);
+    p[n++] = TN(g.ca_sc_w, D, D, D, s.dsc, D, s.ctx_c, D, TB);
+    p[n++] = TN(g.ca_tc_w, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.emb_all, D, TB);
+    p[n++] = TN(g.ca_tc_w + D, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.X2, LX2, TB);
+    SET_PROPAGATE(gemm_group(kTN, p, n, st));
+  }
+  {
+    GemmProblem p[8];
+    int n = 0;
+    p[n++] = TN(g.cl_gcn_w, D, D, D, s.dK, D, s.cnew, D, TB);
+    p[n++] = TN(g.cl_gcm_w, D, D, D, s.dK, D, s.sel, D, TB);
+    p[n++] = TN(g.ca_feat_w, D, A, D, s.datt1c, A, s.prev_h, D, B * P);
+    p[n] = TN(g.fc_w, D, V, D, dl.p, dl.ld, s.h2drop, D, TB);
+    p[n].a_inner = dl.inner; p[n].a_ld_inner = dl.ld_inner; p[n].a_row_len = dl.row_len; p[n].a_valid_inner = B;
+    ++n;
+    p[n] = TN(g.fc_b, 1, V, 1, dl.p, dl.ld, s.ones, 1, TB);
+    p[n].a_inner = dl.inner; p[n].a_ld_inner = dl.ld_inner; p[n].a_row_len = dl.row_len; p[n].a_valid_inner = B;
+    ++n;
+    SET_PROPAGATE(gemm_group(kTN, p, n, st));
+  }
+  SET_PROPAGATE(colsum(s.dG1, 4 * D, TB, 4 * D, g.al_bih, 1, st));
+  SET_PROPAGATE(colsum(s.dG1, 4 * D, TB, 4 * D, g.al_bhh, 1, st));
+  SET_PROPAGATE(colsum(s.dG2, 4 * D, TB, 4 * D, g.cl_x2h_b, 1, st));
+  SET_PROPAGATE(colsum(s.dG2, 4 * D, TB, 4 * D, g.cl_h2h_b, 1, st));
+  SET_PROPAGATE(colsum(s.dS2, LS2, TB, A, g.ca_dec_b, 1, st));
+  SET_PROPAGATE(colsum(s.dS2 + A, LS2, TB, A, g.va_dec_b, 1, st));
+  SET_PROPAGATE(colsum(s.dS2 + 2 * A, LS2, TB, D, g.ca_gate_b, 1, st));
+  SET_PROPAGATE(colsum(s.dS2 + 2 * A + D, LS2, TB, D, g.ca_tc_b, 1, st));
+  SET_PROPAGATE(colsum(s.dsc, D, TB, D, g.ca_sc_b, 1, st));
+  SET_PROPAGATE(colsum(s.dK, D, TB, D, g.cl_gcn_b, 1, st));
+  SET_PROPAGATE(colsum(s.dK, D, TB, D, g.cl_gcm_b, 1, st));
+  SET_PROPAGATE(colsum(s.datt1c, A, B * P, A, g.ca_feat_b, 1, st));
+  {  // d prev_h also flows through cap_features_att
+    GemmProblem p = gemm_problem(B * P, D, s.dprev_h, D);
+    gemm_add_seg(p, s.datt1c, A, w.ca_feat_w, D, A);
+    p.beta = 1;
+    SET_PROPAGATE(gemm(kNN, p, st));
+  }
+  // ---- visual feature path
+  if (c.s.train) {
+    const int TBR = T * B * R;
+    GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_t, D, TBR);
+    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(colsum(s.datt1, A, TBR, A, g.va_feat_b, 1, st));
+    GemmProblem px = gemm_problem(TBR, D, s.dfe_t, D);
+    gemm_add_seg(px, s.datt1, A, w.va_feat_w, D, A);
+    SET_PROPAGATE(gemm(kNN, px, st));
+    SET_PROPAGATE(vis_dropout_bwd(s.fe_pre, s.dfe_t, s.dfe_pre, dl.row_len, T, B, R, D, c.seed, st));
+  } else {
+    GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_pre, D, B * R);
+    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(colsum(s.datt1, A, B * R, A, g.va_feat_b, 1, st));
+    GemmProblem px = gemm_problem(B * R, D, s.dfe_pre, D);
+    gemm_add_seg(px, s.datt1, A, w.va_feat_w, D, A);
+    SET_PROPAGATE(gemm(kNN, px, st));
+    SET_PROPAGATE(relu_bwd_inplace(s.dfe_pre, s.fe_pre, (long)B * R * D, st));
+  }
+  {
+    GemmProblem pw = TN(g.va_emb_w, F, D, F, s.dfe_pre, D, feats, F, B * R);
+    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(colsum(s.dfe_pre, D, B * R, D, g.va_emb_b, 1, st));
+  }
+  // ---- caption encoder BPTT (reverse of editnet.py:333-341)
+  SET_PROPAGATE(tanh_bwd_inplace(s.dfh, s.fh, (long)B * D, st));
+  {
+    GemmProblem pw = TN(g.enc_aff_w, D, D, D, s.dfh, D, s.enc_h + (size_t)P * B * D, D, B);
+    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(colsum(s.dfh, D, B, D, g.enc_aff_b, 1, st));
+    GemmProblem px = gemm_problem(B, D, s.dh_last, D);
+    gemm_add_seg(px, s.dfh, D, w.enc_aff_w, D, D);
+    SET_PROPAGATE(gemm(kNN, px, st));
+  }
+  for (int t = P - 1; t >= 0; --t) {
+    const size_t tb = (size_t)t * B;
+    SET_PROPAGATE(enc_lstm_bwd(s.enc_gates + tb * 4 * D, s.enc_c + tb * D, s.enc_c + (tb + B) * D, s.dh_run,
+                               s.dc_run, s.dprev_h, s.dprev_m, (long)P * D, s.dh_last, prev_len, t,
+                               s.denc_g + tb * 4 * D, B, D, st));
+    if (t > 0) {
+      GemmProblem p = gemm_problem(B, D, s.dh_run, D);
+      gemm_add_seg(p, s.denc_g + tb * 4 * D, 4 * D, w.enc_h2h_w, D, 4 * D);
+      SET_PROPAGATE(gemm(kNN, p, st));
+    }
+  }
+  {
+    GemmProblem p[2];
+    p[0] = TN(g.enc_x2h_w, D, 4 * D, D, s.denc_g, 4 * D, s.emb_prev, D, P * B);
+    p[1] = TN(g.enc_h2h_w, D, 4 * D, D, s.denc_g, 4 * D, s.enc_h, D, P * B);
+    SET_PROPAGATE(gemm_group(kTN, p, 2, st));
+    SET_PROPAGATE(colsum(s.denc_g, 4 * D, P * B, 4 * D, g.enc_x2h_b, 1, st));
+    SET_PROPAGATE(colsum(s.denc_g, 4 * D, P * B, 4 * D, g.enc_h2h_b, 1, st));
+    GemmProblem px = gemm_problem(P * B, D, s.demb_prev, D);
+    gemm_add_seg(px, s.denc_g, 4 * D, w.enc_x2h_w, D, 4 * D);
+    SET_PROPAGATE(gemm(kNN, px, st));
+    SET_PROPAGATE(embed_bwd(prev, c.s.Wp, 1, s.emb_prev, s.demb_prev, g.embed, V, P, B, D, c.s.train, nullptr, st));
+  }
+  return SET_OK;
+}
+
+int batch_sizes(const SetSeqShape& s, const int* dec_len_host, std::vector<int>& bt) {
+  bt.assign(s.T, 0);
+  for (int i = 0; i < s.B; ++i) {
+    SET_REQUIRE(dec_len_host[i] >= 0 && dec_len_host[i] <= s.T, "decode_len out of range");
+    if (i > 0) SET_REQUIRE(dec_len_host[i] <= dec_len_host[i - 1], "decode_len must be sorted descending");
+    for (int t = 0; t < dec_len_host[i]; ++t) bt[t]++;
+  }
+  return SET_OK;
+}
+
+// ------------------------------------------------------------------ rollout sampling
+// log_softmax + greedy / multinomial / forced choice + finished bookkeeping for one step
+// (editnet_rl.py:514-546).  One block per row.
+__global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int V, int B, int T, int t,
+                                                          int mode, const int64_t* __restrict__ forced,
+                                                          uint64_t seed, int64_t end_token,
+                                                          int* __restrict__ unfinished, int* __restrict__ unf_count,
+                                                          int64_t* __restrict__ it_out, int64_t* __restrict__ seq,
+                                                          float* __restrict__ slp, float* __restrict__ lse_out,
+                                                          int64_t* __restrict__ tok_raw) {
+  __shared__ float red[40];
+  __shared__ float csum[256];
+  __shared__ int s_idx;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const bool live = (t == 0) || (unf_count[t] > 0);   // the reference leaves the loop once every row finished (:546)
+  if (!live) {
+    if (tid == 0) { it_out[i] = 0; tok_raw[(long)t * B + i] = -1; }
+    return;
+  }
+  const float* x = logits + (long)i * V;
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int v = tid; v < V; v += blockDim.x) {
+    const float xv = x[v];
+    if (xv > m) { m = xv; am = v; }
+  }
+  // block arg-max (first index on ties)
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  __shared__ float wm[8];
+  __shared__ int wa[8];
+  if ((tid & 31) == 0) { wm[tid >> 5] = m; wa[tid >> 5] = am; }
+  __syncthreads();
+  m = wm[0]; am = wa[0];
+  for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+    if (wm[k] > m || (wm[k] == m && wa[k] < am)) { m = wm[k]; am = wa[k]; }
+  float part = 0.f;
+  for (int v = tid; v < V; v += blockDim.x) part += expf(x[v] - m);
+  const float sum = block_sum(part, red);
+  const float lse = m + logf(sum);
+  int tok = am;
+  if (mode == 1) {
+    // inverse CDF over contiguous per-thread chunks
+    const float u = philox_uniform(seed, kSiteSample, (uint64_t)t * B + i) * sum;
+    const int chunk = (V + blockDim.x - 1) / blockDim.x;
+    const int v0 = tid * chunk, v1 = min(V, v0 + chunk);
+    float loc = 0.f;
+    for (int v = v0; v < v1; ++v) loc += expf(x[v] - m);
+    csum[tid] = loc;
+    if (tid == 0) s_idx = V - 1;
+    __syncthreads();
+    if (tid == 0) {
+      float run = 0.f;
+      int sel_t = blockDim.x - 1;
+      for (int k = 0; k < (int)blockDim.x; ++k) {
+        if (run + csum[k] > u) { sel_t = k; break; }
+        run += csum[k];
+      }
+      const int a0 = sel_t * chunk, a1 = min(V, a0 + chunk);
+      int pick = max(a1 - 1, 0);
+      for (int v = a0; v < a1; ++v) {
+        run += expf(x[v] - m);
+        if (run > u) { pick = v; break; }
+      }
+      s_idx = pick;
+    }
+    __syncthreads();
+    tok = s_idx;
+  } else if (mode == 2) {
+    tok = (int)forced[(long)i * T + t];
+  }
+  if (tid == 0) {
+    const float lp = x[tok] - m - logf(sum);
+    int64_t tk = (tok == end_token) ? 0 : tok;
+    const int unf = (t == 0) ? (tk > 0) : (unfinished[i] && tk > 0);
+    if (!unf) tk = 0;
+    seq[(long)i * T + t] = tk;
+    slp[(long)i * T + t] = lp;
+    unfinished[i] = unf;
+    it_out[i] = tk;
+    lse_out[(long)t * B + i] = lse;
+    tok_raw[(long)t * B + i] = tok;
+    if (unf) atomicAdd(&unf_count[t + 1], 1);
+  }
+}
+
+// d logits[t][i][v] = d_slp[i][t] * (1[v == tok] - softmax_v)   (in place over the saved logits)
+__global__ void rollout_dlogits_kernel(float* __restrict__ logits, int V, int B, int T,
+                                       const float* __restrict__ d_slp, const float* __restrict__ lse,
+                                       const int64_t* __restrict__ tok_raw) {
+  const long row = blockIdx.x;  // t*B + i
+  const int t = (int)(row / B), i = (int)(row % B);
+  const int64_t tok = tok_raw[row];
+  const float g = (tok >= 0) ? d_slp[(long)i * T + t] : 0.f;
+  const float l = lse[row];
+  float* x = logits + row * V;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float pr = (tok >= 0) ? expf(x[v] - l) : 0.f;
+    x[v] = g * ((v == tok ? 1.f : 0.f) - pr);
+  }
+}
+
+// packed cross-entropy (editnet.py:571-577)
+__global__ void __launch_bounds__(256) xe_loss_kernel(int B, int T, int V, int Wc, const float* __restrict__ pred,
+                                                      const int64_t* __restrict__ caps,
+                                                      const int* __restrict__ dec_len, float inv_count,
+                                                      float* __restrict__ loss_out, float* __restrict__ dpred) {
+  __shared__ float red[40];
+  const int i = blockIdx.x / T, t = blockIdx.x % T;
+  const long off = ((long)i * T + t) * V;
+  const bool valid = dec_len[i] > t;
+  if (!valid) {
+    if (dpred) for (int v = threadIdx.x; v < V; v += blockDim.x) dpred[off + v] = 0.f;
+    return;
+  }
+  if (inv_count <= 0.f) {
+    int cnt = 0;
+    for (int k = 0; k < B; ++k) cnt += min(dec_len[k], T);
+    inv_count = 1.f / (float)cnt;
+  }
+  const float* x = pred + off;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+  m = warp_max(m);
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = wm[0];
+  for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmaxf(m, wm[k]);
+  float part = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) part += expf(x[v] - m);
+  const float sum = block_sum(part, red);
+  const float lse = m + logf(sum);
+  const int64_t tgt = caps[(long)i * Wc + t + 1];
+  if (threadIdx.x == 0) atomicAdd(loss_out, (lse - x[tgt]) * inv_count);
+  if (dpred) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float pr = expf(x[v] - lse);
+      dpred[off + v] = (pr - (v == tgt ? 1.f : 0.f)) * inv_count;
+    }
+  }
+}
+
+__global__ void xe_count_kernel(int B, int T, const int* __restrict__ dec_len, float* __restrict__ loss_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int cnt = 0;
+    for (int k = 0; k < B; ++k) cnt += min(dec_len[k], T);
+    loss_out[1] = (float)cnt;
+  }
+}
+
+// RewardCriterion (editnet_rl.py:557-573), single block
+__global__ void __launch_bounds__(256) reward_kernel(int B, int T, const float* __restrict__ slp,
+                                                     const int64_t* __restrict__ seq, const float* __restrict__ reward,
+                                                     float* __restrict__ loss_out, float* __restrict__ dlp) {
+  __shared__ float red[40];
+  float num = 0.f, den = 0.f;
+  for (int x = threadIdx.x; x < B * T; x += blockDim.x) {
+    const int t = x % T;
+    const float mk = (t == 0) ? 1.f : (seq[x - 1] > 0 ? 1.f : 0.f);
+    num += -slp[x] * reward[x] * mk;
+    den += mk;
+  }
+  num = block_sum(num, red);
+  den = block_sum(den, red);
+  if (threadIdx.x == 0) loss_out[0] = num / den;
+  if (dlp)
+    for (int x = threadIdx.x; x < B * T; x += blockDim.x) {
+      const int t = x % T;
+      const float mk = (t == 0) ? 1.f : (seq[x - 1] > 0 ? 1.f : 0.f);
+      dlp[x] = -reward[x] * mk / den;
+    }
+}
+
+}  // namespace
+}  // namespace set
+
+using namespace set;
+
+extern "C" {
+
+size_t set_editnet_workspace_bytes(const SetDims* dims, const SetSeqShape* shape) {
+  if (check_args(dims, shape) != SET_OK) return 0;
+  Arena ar;
+  Ws ws;
+  layout(*dims, *shape, ar, ws);
+  return ws.total;
+}
+
+int set_editnet_workspace_lookup(const SetDims* dims, const SetSeqShape* shape, const char* name, size_t* offset,
+                                 size_t* bytes) {
+  SET_PROPAGATE(check_args(dims, shape));
+  Arena ar;
+  Ws ws;
+  layout(*dims, *shape, ar, ws);
+  for (const auto& e : ar.entries)
+    if (e.name == name) { *offset = e.off; *bytes = e.bytes; return SET_OK; }
+  set_record_error("unknown workspace buffer name");
+  return SET_ERR_ARG;
+}
+
+int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                           const float* feats, const float* image_mean, const int64_t* caps,
+                           const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                           uint64_t seed, float* predictions, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
+  SET_REQUIRE(feats && caps && decode_len_host && prev && prev_len && predictions, "null input");
+  SET_REQUIRE(shape->Wc > shape->T, "caption width must exceed T");
+  std::vector<int> bt;
+  SET_PROPAGATE(batch_sizes(*shape, decode_len_host, bt));
+  const int B = shape->B, T = shape->T, D = dims->D, V = dims->V;
+  SET_PROPAGATE(prepare_common(c, feats, image_mean, prev, prev_len));
+  SET_CHECK_CUDA(cudaMemcpyAsync(c.ws.dec_len, decode_len_host, sizeof(int) * B, cudaMemcpyHostToDevice, c.st));
+  SET_PROPAGATE(embed_fwd(caps, shape->Wc, 1, w->embed, V, c.ws.emb_all, T, B, D, shape->train, seed, kSiteEmb, 0, B, 1,
+                          c.st));
+  SET_PROPAGATE(project_words(c, 0, T));
+  for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
+  // vocabulary projection for all decoded rows at once (editnet.py:545-546), written batch-major
+  SET_CHECK_CUDA(cudaMemsetAsync(predictions, 0, sizeof(float) * (size_t)B * T * V, c.st));
+  GemmProblem p = gemm_problem(T * B, V, predictions, V);
+  gemm_add_seg(p, c.ws.h2drop, D, w->fc_w, D, D);
+  p.bias = w->fc_b;
+  p.c_inner = B; p.c_ld_inner = (long)T * V; p.c_row_len = c.ws.dec_len; p.c_valid_inner = B;
+  SET_PROPAGATE(gemm(kNT, p, c.st));
+  return SET_OK;
+}
+
+int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                            const SetEditNetParams* grads, const float* feats, const int64_t* caps,
+                            const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                            uint64_t seed, const float* d_predictions, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
+  SET_REQUIRE(grads && feats && caps && decode_len_host && prev && prev_len && d_predictions, "null input");
+  std::vector<int> bt;
+  SET_PROPAGATE(batch_sizes(*shape, decode_len_host, bt));
+  DLogits dl;
+  dl.p = d_predictions; dl.ld = dims->V; dl.inner = shape->B; dl.ld_inner = (long)shape->T * dims->V;
+  dl.row_len = c.ws.dec_len;  // uploaded by the forward call
+  return backward_core(c, *grads, feats, caps, shape->Wc, 1, prev, prev_len, bt.data(), dl);
+}
+
+int set_xe_loss(int B, int T, int V, int Wc, const float* predictions, const int64_t* caps,
+                const int* decode_len_dev, float inv_count, float* loss_out, float* d_predictions,
+                void* stream) {
+  SET_REQUIRE(B > 0 && T > 0 && V > 1 && Wc > T && predictions && caps && decode_len_dev && loss_out, "bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SET_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, 2 * sizeof(float), st));
+  xe_loss_kernel<<<B * T, 256, 0, st>>>(B, T, V, Wc, predictions, caps, decode_len_dev, inv_count, loss_out,
+                                        d_predictions);
+  SET_CHECK_CUDA(cudaGetLastError());
+  xe_count_kernel<<<1, 32, 0, st>>>(B, T, decode_len_dev, loss_out);
+  SET_CHECK_CUDA(cudaGetLastError());
+  return SET_OK;
+}
+
+int set_editnet_rollout(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                        const float* feats, const float* image_mean, const int64_t* prev,
+                        const int64_t* prev_len, int64_t start_token, int64_t end_token, int mode,
+                        const int64_t* forced, uint64_t seed, int64_t* seq, float* seq_logprobs,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
+  SET_REQUIRE(feats && prev && prev_len && seq && seq_logprobs, "null input");
+  SET_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || forced != nullptr), "bad mode");
+  const int B = shape->B, T = shape->T, D = dims->D, V = dims->V;
+  Ws& s = c.ws;
+  SET_PROPAGATE(prepare_common(c, feats, image_mean, prev, prev_len));
+  SET_CHECK_CUDA(cudaMemsetAsync(seq, 0, sizeof(int64_t) * (size_t)B * T, c.st));
+  SET_CHECK_CUDA(cudaMemsetAsync(seq_logprobs, 0, sizeof(float) * (size_t)B * T, c.st));
+  fill_i64_kernel<<<1, 256, 0, c.st>>>(s.it, B, start_token);
+  SET_CHECK_CUDA(cudaGetLastError());
+  for (int t = 0; t < T; ++t) {
+    SET_PROPAGATE(embed_fwd(s.it + (size_t)t * B, 1, 0, w->embed, V, s.emb_all + (size_t)t * B * D, 1, B, D,
+                            shape->train, seed, kSiteEmb, (long)t * B, 0, 1, c.st));
+    SET_PROPAGATE(project_words(c, t, 1));
+    SET_PROPAGATE(step_forward(c, feats, t, B));
+    float* lg = shape->train ? s.logits + (size_t)t * B * V : s.logits;
+    GemmProblem p = gemm_problem(B, V, lg, V);
+    gemm_add_seg(p, s.h2drop + (size_t)t * B * D, D, w->fc_w, D, D);
+    p.bias = w->fc_b;
+    SET_PROPAGATE(gemm(kNT, p, c.st));
+    sample_step_kernel<<<B, 256, 0, c.st>>>(lg, V, B, T, t, mode, forced, seed, end_token, s.unfinished,
+                                            s.unf_count, s.it + (size_t)(t + 1) * B, seq, seq_logprobs, s.lse, s.tok_raw);
+    SET_CHECK_CUDA(cudaGetLastError());
+  }
+  return SET_OK;
+}
+
+int set_editnet_rollout_backward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                                 const SetEditNetParams* grads, const float* feats, const int64_t* prev,
+                                 const int64_t* prev_len, uint64_t seed, const float* d_seq_logprobs,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
+  SET_REQUIRE(shape->train, "rollout backward needs a train-mode forward (activations kept)");
+  SET_REQUIRE(grads && feats && prev && prev_len && d_seq_logprobs, "null input");
+  const int B = shape->B, T = shape->T, V = dims->V;
+  Ws& s = c.ws;
+  rollout_dlogits_kernel<<<T * B, 256, 0, c.st>>>(s.logits, V, B, T, d_seq_logprobs, s.lse, s.tok_raw);
+  SET_CHECK_CUDA(cudaGetLastError());
+  std::vector<int> bt(T, B);
+  DLogits dl;
+  dl.p = s.logits; dl.ld = V; dl.inner = 0; dl.ld_inner = 0; dl.row_len = nullptr;
+  // the embedding of step t was looked up from the token fed at step t (`it[t]`: <start>, then the
+  // previous step's output token after the <end>/finished rewrite, editnet_rl.py:531-540)
+  return backward_core(c, *grads, feats, s.it, 1, B, prev, prev_len, bt.data(), dl);
+}
+
+int set_reward_criterion(int B, int T, const float* seq_logprobs, const int64_t* seq, const float* reward,
+                         float* loss_out, float* d_logprobs, void* stream) {
+  SET_REQUIRE(B > 0 && T > 0 && seq_logprobs && seq && reward && loss_out, "bad args");
+  reward_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(B, T, seq_logprobs, seq, reward, loss_out,
+                                                                       d_logprobs);
+  SET_CHECK_CUDA(cudaGetLastError());
+  return SET_OK;
+}
+
+int set_dropout_keep_mask(float* out, size_t n, uint64_t seed, int site, size_t base, void* stream) {
+  SET_REQUIRE(out != nullptr, "null out");
+  return dropout_keep_mask(out, (long)n, seed, (uint32_t)site, (long)base, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,
+             const float* bias, float* C, long ldc, int beta, int act, void* stream) {
+  GemmProblem p = gemm_problem(M, N, C, ldc);
+  gemm_add_seg(p, A, lda, Bm, ldb, K);
+  p.bias = bias; p.beta = beta; p.act = act;
+  return gemm(mode, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// GEMM front-end for the decode path: every dense contraction on the path goes
+// through set::gemm_group().  Three operand layouts cover forward (NT), the dX pass
+// (NN) and the dW pass (TN); up to four K-segments let a logical concatenation
+// ([h2;h1], [att_cap|att_img], ...) be consumed in place without materialising it.
+#pragma once
+#include "common.cuh"
+
+namespace set {
+
+enum GemmMode { kNT = 0, kNN = 1, kTN = 2 };
+// kNT: C[m,n] = sum_k A[row(m) + k]   * B[n*ldb + k]      (x @ W^T, W row-major [N,K])
+// kNN: C[m,n] = sum_k A[row(m) + k]   * B[k*ldb + n]      (dy @ W)
+// kTN: C[m,n] = sum_k A[row(k) + m]   * B[k*ldb + n]      (dy^T @ x)
+// row(x) = x*lda, or with a_inner>0: (x / a_inner)*lda + (x % a_inner)*a_ld_inner
+// (time-major row index over a batch-major [B][T][.] tensor).
+
+struct GemmSeg {
+  const float* A; long lda;
+  const float* B; long ldb;
+  int K;
+};
+
+struct GemmProblem {
+  int M, N, nseg;
+  GemmSeg seg[4];
+  int a_inner; long a_ld_inner;          // two-level A rows (all segments)
+  const int* a_row_len; int a_valid_inner;  // A row x valid iff a_row_len[x % vi] > x / vi, else reads 0
+  const float* bias; const float* bias2; // [N], added once (ignored when null)
+  const float* add; long ldadd; int add_mod;  // + add[(add_mod ? m % add_mod : m)*ldadd + n]
+  float* C; long ldc;
+  int c_inner; long c_ld_inner;          // two-level C rows
+  const int* c_row_len; int c_valid_inner;  // invalid C rows are not written
+  int beta;                              // 1: C += result
+  int act;                               // 0 none, 1 relu, 2 tanh
+};
+
+struct GemmGroup {
+  int n;
+  int tile_start[9];
+  GemmProblem p[8];
+};
+
+inline GemmProblem gemm_problem(int M, int N, float* C, long ldc) {
+  GemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.C = C; p.ldc = ldc;
+  return p;
+}
+inline void gemm_add_seg(GemmProblem& p, const float* A, long lda, const float* B, long ldb, int K) {
+  if (K <= 0 || A == nullptr) return;
+  GemmSeg& s = p.seg[p.nseg++];
+  s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K;
+}
+
+// Launch up to 8 independent problems of one mode in a single grid.
+int gemm_group(int mode, const GemmProblem* probs, int n, cudaStream_t stream);
+inline int gemm(int mode, const GemmProblem& p, cudaStream_t stream) { return gemm_group(mode, &p, 1, stream); }
+
+// column sums: out[n] (+)= sum_m X[m*ld + n]
+int colsum(const float* X, long ld, int M, int N, float* out, int beta, cudaStream_t stream);
+
+}  // namespace set

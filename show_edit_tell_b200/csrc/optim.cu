@@ -1,0 +1,90 @@
+// Error reporting, version, and the fused optimizer tail of the train step:
+// global-norm clip + Adam over one flat buffer (train() tail, editnet.py:580-581).
+#include <mutex>
+#include <string>
+
+#include "../../include/set_b200.h"
+#include "common.cuh"
+
+namespace {
+std::mutex g_err_mu;
+std::string g_err = "";
+}  // namespace
+
+extern "C" void set_record_error(const char* msg) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = msg ? msg : "";
+}
+
+extern "C" const char* set_last_error(void) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  static thread_local std::string copy;
+  copy = g_err;
+  return copy.c_str();
+}
+
+extern "C" int set_version(void) { return 100; }
+
+namespace set {
+namespace {
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float red[40];
+  float s = 0.f;
+  const size_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n4; x += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g4 + x);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (size_t x = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n;
+       x += (size_t)gridDim.x * blockDim.x)
+    s += g[x] * g[x];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// torch.optim.Adam (defaults, no amsgrad / weight decay) after clip_grad_norm_:
+//   g *= min(1, max_norm / (total_norm + 1e-6));  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
+//   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, size_t n,
+                                                   float lr, float b1, float b2, float eps, float bc1, float bc2s,
+                                                   float max_norm, float grad_scale,
+                                                   const float* __restrict__ count_dev,
+                                                   float* __restrict__ scratch) {
+  if (count_dev) grad_scale /= count_dev[0];
+  const float total = sqrtf(scratch[0]) * fabsf(grad_scale);
+  const float coef = fminf(max_norm / (total + 1e-6f), 1.0f) * grad_scale;
+  if (blockIdx.x == 0 && threadIdx.x == 0) scratch[1] = total;
+  const float step = lr / bc1;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+    const float gv = g[x] * coef;
+    const float mv = b1 * m[x] + (1.f - b1) * gv;
+    const float vv = b2 * v[x] + (1.f - b2) * gv * gv;
+    m[x] = mv;
+    v[x] = vv;
+    p[x] -= step * mv / (sqrtf(vv) / bc2s + eps);
+  }
+}
+
+}  // namespace
+}  // namespace set
+
+extern "C" int set_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                             int step, float lr, float beta1, float beta2, float eps, float max_norm,
+                             float grad_scale, const float* count_dev, float* scratch, void* stream) {
+  SET_REQUIRE(params && grads && exp_avg && exp_avg_sq && scratch && step >= 1, "bad args");
+  SET_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grads must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SET_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st));
+  const int blocks = 148 * 8;
+  set::sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, scratch);
+  SET_CHECK_CUDA(cudaGetLastError());
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  set::adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2s,
+                                           max_norm, grad_scale, count_dev, scratch);
+  SET_CHECK_CUDA(cudaGetLastError());
+  return SET_OK;
+}

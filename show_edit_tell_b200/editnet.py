@@ -1,0 +1,380 @@
+"""EditNet host side: the reference's module surface over the CUDA C ABI.
+
+Class names, constructor signatures, sub-module attribute names and `state_dict` keys
+are those of /root/reference/editnet.py:210-477 (and `eval/eval xe/editnet.py`, the
+class-only copy checkpoints are unpickled against), so `DecoderC` drops into the
+reference's `train()` / checkpoint code.  The arithmetic of `forward` runs entirely
+in libset_b200.so (hand-written sm_100a kernels); torch only owns memory, streams and the
+autograd edge.  There is no CPU path: calling `forward` without the built library or
+without a CUDA device raises.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import EDITNET_FIELDS, SetDims, SetEditNetParams, SetSeqShape, check, ptr
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _draw_seed():
+    # one 62-bit seed per call from torch's CPU generator -> torch.manual_seed governs dropout
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+# --------------------------------------------------------------------- parameter shells
+class LSTMCellC(nn.Module):
+    """Parameter container of the encoder cell (editnet.py:210-244)."""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.input_size = input_size
+        self.x2h = nn.Linear(input_size, 4 * hidden_size)
+        self.h2h = nn.Linear(hidden_size, 4 * hidden_size)
+        self.tanh = nn.Tanh()
+        self.init_parameters()
+
+    def init_parameters(self):
+        std = 1.0 / math.sqrt(self.hidden_size)
+        for p in self.parameters():
+            p.data.uniform_(-std, std)
+
+
+class CopyLSTMCellC(nn.Module):
+    """Parameter container of the copy-LSTM (editnet.py:247-285)."""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.input_size = input_size
+        self.x2h = nn.Linear(input_size, 4 * hidden_size)
+        self.h2h = nn.Linear(hidden_size, 4 * hidden_size)
+        self.gate_cnew = nn.Linear(hidden_size, hidden_size)
+        self.gate_cmem = nn.Linear(hidden_size, hidden_size)
+        self.tanh = nn.Tanh()
+        self.init_parameters()
+
+    def init_parameters(self):
+        std = 1.0 / math.sqrt(self.hidden_size)
+        for p in self.parameters():
+            p.data.uniform_(-std, std)
+
+
+class EmbeddingC(nn.Module):
+    """editnet.py:288-304"""
+
+    def __init__(self, word_map, emb_dim):
+        super().__init__()
+        self.emb_dim = emb_dim
+        self.word_map = word_map
+        self.embedding = nn.Embedding(len(word_map), self.emb_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(0.5)
+
+
+class CaptionEncoderC(nn.Module):
+    """editnet.py:307-348"""
+
+    def __init__(self, vocab_size, emb_dim, enc_hid_dim, embed):
+        super().__init__()
+        self.vocab_size = vocab_size
+        self.emb_dim = emb_dim
+        self.enc_hid_dim = enc_hid_dim
+        self.embed = embed
+        self.lstm_encoder_cell = LSTMCellC(emb_dim, enc_hid_dim)
+        self.affine_hn = nn.Linear(enc_hid_dim, enc_hid_dim)
+        self.tanh = nn.Tanh()
+
+
+class CaptionAttentionC(nn.Module):
+    """editnet.py:351-381"""
+
+    def __init__(self, caption_features_dim, decoder_dim, attention_dim):
+        super().__init__()
+        self.cap_features_att = nn.Linear(caption_features_dim, attention_dim)
+        self.cap_decoder_att = nn.Linear(decoder_dim, attention_dim)
+        self.cap_full_att = nn.Linear(attention_dim, 1)
+        self.context_gate = nn.Linear((caption_features_dim * 2) + decoder_dim, caption_features_dim)
+        self.sc_affine = nn.Linear(caption_features_dim, caption_features_dim)
+        self.tc_affine = nn.Linear(decoder_dim * 2, caption_features_dim)
+        self.tanh = nn.Tanh()
+
+
+class SelectC(nn.Module):
+    """editnet.py:383-421 (no parameters)"""
+
+    def __init__(self, prev_caption_dim, decoder_dim):
+        super().__init__()
+
+
+class VisualAttentionC(nn.Module):
+    """editnet.py:424-447"""
+
+    def __init__(self, image_features_dim, decoder_dim, attention_dim):
+        super().__init__()
+        self.att_embed = nn.Sequential(nn.Linear(image_features_dim, decoder_dim), nn.ReLU(), nn.Dropout(0.5))
+        self.features_att = nn.Linear(decoder_dim, attention_dim)
+        self.decoder_att = nn.Linear(decoder_dim, attention_dim)
+        self.full_att = nn.Linear(attention_dim, 1)
+        self.softmax = nn.Softmax(dim=1)
+
+
+# ------------------------------------------------------------------------- autograd edge
+class _XEFunction(torch.autograd.Function):
+    """predictions = f(parameters): forward/backward are one C call each."""
+
+    @staticmethod
+    def forward(ctx, mod, call, *params):
+        ctx.mod, ctx.call = mod, call
+        return mod._xe_forward_raw(call)
+
+    @staticmethod
+    def backward(ctx, dpred):
+        mod, call = ctx.mod, ctx.call
+        flat_grad = torch.zeros_like(mod._flat)
+        mod._xe_backward_raw(call, dpred.contiguous(), flat_grad)
+        return (None, None) + tuple(mod._views(flat_grad))
+
+
+class _RolloutFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, call, *params):
+        ctx.mod, ctx.call = mod, call
+        seq, slp = mod._rollout_raw(call)
+        ctx.mark_non_differentiable(seq)
+        return seq, slp
+
+    @staticmethod
+    def backward(ctx, dseq, dslp):
+        mod, call = ctx.mod, ctx.call
+        flat_grad = torch.zeros_like(mod._flat)
+        mod._rollout_backward_raw(call, dslp.contiguous(), flat_grad)
+        return (None, None) + tuple(mod._views(flat_grad))
+
+
+class _Call:
+    """everything one forward/backward pair shares"""
+    pass
+
+
+class EditNetBase(nn.Module):
+    """DecoderC.__init__ of editnet.py:451-471 plus the plumbing shared by the XE, RL and
+    adaptive front-ends."""
+
+    ADAPTIVE = False
+
+    def __init__(self, word_map, decoder_dim=1024, caption_features_dim=1024, emb_dim=1024, attention_dim=512,
+                 image_features_dim=2048):
+        super().__init__()
+        if not (decoder_dim == caption_features_dim == emb_dim):
+            raise ValueError("the reference's concatenations require decoder_dim == caption_features_dim == "
+                             "emb_dim (editnet.py:359-361,468-469)")
+        self.vocab_size = len(word_map)
+        self.dropout = nn.Dropout(0.5)
+        self.decoder_dim = decoder_dim
+        self.attention_dim = attention_dim
+        self.image_features_dim = image_features_dim
+        self.embed = EmbeddingC(word_map, emb_dim)
+        self.caption_encoder = CaptionEncoderC(len(word_map), emb_dim, caption_features_dim, self.embed)
+        self.caption_attention = CaptionAttentionC(caption_features_dim, decoder_dim, attention_dim)
+        self.visual_attention = VisualAttentionC(image_features_dim, decoder_dim, attention_dim)
+        self.select = SelectC(caption_features_dim, decoder_dim)
+        self.attention_lstm = nn.LSTMCell((emb_dim * 3) + image_features_dim, decoder_dim)
+        self.copy_lstm = CopyLSTMCellC((emb_dim * 2) + image_features_dim, decoder_dim)
+        self.tanh = nn.Tanh()
+        self.fc = nn.Linear(decoder_dim, self.vocab_size)
+        self._flat = None
+        self._offsets = None
+        self._struct = None
+        self.last_seed = None
+
+    def init_hidden_state(self, batch_size):
+        dev = self.fc.weight.device
+        return (torch.zeros(batch_size, self.decoder_dim, device=dev),
+                torch.zeros(batch_size, self.decoder_dim, device=dev))
+
+    # ---- flat parameter storage: every parameter is a view into one buffer, so the optimizer
+    # tail and the data-parallel all-reduce see a single tensor
+    def _ordered_params(self):
+        return [self.get_parameter(key) for _, key in EDITNET_FIELDS]
+
+    def flatten_parameters(self):
+        params = self._ordered_params()
+        dev = params[0].device
+        if self._flat is not None and self._flat.device == dev:
+            base = self._flat.data_ptr()
+            if all(p.data_ptr() == base + 4 * o for p, o in zip(params, self._offsets)):
+                return self._flat
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(params, offs):
+            view = flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self._flat, self._offsets = flat, offs
+        st = SetEditNetParams()
+        for (name, _), p in zip(EDITNET_FIELDS, params):
+            setattr(st, name, p.data_ptr())
+        self._struct = st
+        return flat
+
+    def _views(self, flat):
+        return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self._ordered_params(), self._offsets)]
+
+    def _struct_for(self, flat):
+        st = SetEditNetParams()
+        for (name, _), v in zip(EDITNET_FIELDS, self._views(flat)):
+            setattr(st, name, v.data_ptr())
+        return st
+
+    def _dims(self):
+        return SetDims(self.vocab_size, self.decoder_dim, self.attention_dim, self.image_features_dim)
+
+    def _require_cuda(self, t):
+        if not t.is_cuda:
+            raise RuntimeError("show_edit_tell_b200 runs on a CUDA device only (no CPU fallback): "
+                               "move the module and its inputs to cuda")
+
+    # ---- teacher-forced path -------------------------------------------------------------
+    def _prepare_xe(self, image_features, image_mean, encoded_captions, caption_lengths,
+                    encoded_previous_captions, previous_cap_length, seed=None):
+        self._require_cuda(image_features)
+        self.flatten_parameters()
+        lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)        # editnet.py:488
+        call = _Call()
+        call.feats = image_features[sort_ind].contiguous().float()
+        call.image_mean = None if image_mean is None else image_mean[sort_ind].contiguous().float()
+        call.caps = encoded_captions[sort_ind].contiguous()
+        call.prev = encoded_previous_captions[sort_ind].contiguous()
+        call.prev_len = previous_cap_length[sort_ind].contiguous().view(-1)
+        host = torch.cat([lens - 1, call.prev_len.max().view(1)]).tolist()                # one D2H sync
+        call.decode_lengths = host[:-1]
+        P = int(host[-1])
+        B, Wc = call.caps.shape
+        T = max(call.decode_lengths)
+        call.shape = SetSeqShape(B, call.feats.shape[1], Wc, call.prev.shape[1], P, T, int(self.training),
+                                 int(self.ADAPTIVE))
+        call.dims = self._dims()
+        call.dec_host = (C.c_int * B)(*call.decode_lengths)
+        call.seed = (_draw_seed() if seed is None else seed) if self.training else 0
+        self.last_seed = call.seed
+        nbytes = _lib.lib().set_editnet_workspace_bytes(C.byref(call.dims), C.byref(call.shape))
+        if nbytes == 0:
+            raise RuntimeError("libset_b200: " + _lib.lib().set_last_error().decode())
+        call.ws = torch.empty(nbytes, dtype=torch.uint8, device=call.feats.device)
+        call.sort_ind = sort_ind
+        return call
+
+    def _xe_forward_raw(self, call):
+        s = call.shape
+        pred = torch.empty(s.B, s.T, self.vocab_size, device=call.feats.device, dtype=torch.float32)
+        check(_lib.lib().set_editnet_xe_forward(
+            C.byref(call.dims), C.byref(s), C.byref(self._struct), ptr(call.feats), ptr(call.image_mean),
+            ptr(call.caps), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, ptr(pred), ptr(call.ws),
+            call.ws.numel(), _stream()))
+        return pred
+
+    def _xe_backward_raw(self, call, dpred, flat_grad):
+        g = self._struct_for(flat_grad)
+        check(_lib.lib().set_editnet_xe_backward(
+            C.byref(call.dims), C.byref(call.shape), C.byref(self._struct), C.byref(g), ptr(call.feats),
+            ptr(call.caps), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, ptr(dpred), ptr(call.ws),
+            call.ws.numel(), _stream()))
+
+    def _xe(self, image_features, image_mean, encoded_captions, caption_lengths, encoded_previous_captions,
+            previous_cap_length, use_ss, ss_prob):
+        if use_ss and ss_prob > 0.0:
+            raise NotImplementedError(
+                "scheduled sampling (editnet.py:508-520) is not built yet: call with ss_prob = 0 "
+                "(the reference's own setting for epochs 0-4, editnet.py:812-816)")
+        call = self._prepare_xe(image_features, image_mean, encoded_captions, caption_lengths,
+                                encoded_previous_captions, previous_cap_length)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            pred = _XEFunction.apply(self, call, *self._ordered_params())
+        else:
+            pred = self._xe_forward_raw(call)
+        self._last_call = call
+        return pred, call
+
+    # ---- rollout path -----------------------------------------------------------------------
+    def _prepare_rollout(self, encoded_previous_captions, previous_cap_length, image_features, image_mean, mode,
+                         max_len, start_idx, end_idx, forced=None, seed=None, keep=None):
+        self._require_cuda(image_features)
+        self.flatten_parameters()
+        call = _Call()
+        call.feats = image_features.contiguous().float()
+        call.image_mean = None if image_mean is None else image_mean.contiguous().float()
+        call.prev = encoded_previous_captions.contiguous()
+        call.prev_len = previous_cap_length.contiguous().view(-1)
+        P = int(call.prev_len.max().item())
+        B = call.feats.shape[0]
+        keep = self.training if keep is None else keep
+        call.shape = SetSeqShape(B, call.feats.shape[1], 0, call.prev.shape[1], P, max_len, int(keep),
+                                 int(self.ADAPTIVE))
+        call.dims = self._dims()
+        call.mode, call.start_idx, call.end_idx = mode, start_idx, end_idx
+        call.forced = None if forced is None else forced.contiguous()
+        call.seed = _draw_seed() if seed is None else seed
+        self.last_seed = call.seed
+        nbytes = _lib.lib().set_editnet_workspace_bytes(C.byref(call.dims), C.byref(call.shape))
+        if nbytes == 0:
+            raise RuntimeError("libset_b200: " + _lib.lib().set_last_error().decode())
+        call.ws = torch.empty(nbytes, dtype=torch.uint8, device=call.feats.device)
+        return call
+
+    def _rollout_raw(self, call):
+        s = call.shape
+        dev = call.feats.device
+        seq = torch.empty(s.B, s.T, dtype=torch.int64, device=dev)
+        slp = torch.empty(s.B, s.T, dtype=torch.float32, device=dev)
+        check(_lib.lib().set_editnet_rollout(
+            C.byref(call.dims), C.byref(s), C.byref(self._struct), ptr(call.feats), ptr(call.image_mean),
+            ptr(call.prev), ptr(call.prev_len), call.start_idx, call.end_idx, call.mode, ptr(call.forced), call.seed,
+            ptr(seq), ptr(slp), ptr(call.ws), call.ws.numel(), _stream()))
+        return seq, slp
+
+    def _rollout_backward_raw(self, call, dslp, flat_grad):
+        g = self._struct_for(flat_grad)
+        check(_lib.lib().set_editnet_rollout_backward(
+            C.byref(call.dims), C.byref(call.shape), C.byref(self._struct), C.byref(g), ptr(call.feats),
+            ptr(call.prev), ptr(call.prev_len), call.seed, ptr(dslp), ptr(call.ws), call.ws.numel(), _stream()))
+
+    def rollout(self, word_map, encoded_previous_captions, previous_cap_length, image_features, sample_max,
+                sample_rl, max_len=18, image_mean=None, forced=None, seed=None):
+        """editnet_rl.py:485-549.  `forced` (B,max_len) replays given tokens instead of sampling."""
+        mode = 2 if forced is not None else (1 if sample_rl else 0)
+        want_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        call = self._prepare_rollout(encoded_previous_captions, previous_cap_length, image_features, image_mean,
+                                     mode, max_len, word_map['<start>'], word_map['<end>'], forced, seed,
+                                     keep=self.training)
+        self._last_call = call
+        if want_grad:
+            return _RolloutFunction.apply(self, call, *self._ordered_params())
+        return self._rollout_raw(call)
+
+    # debugging / tests: a named workspace buffer of the last call as a float tensor
+    def workspace_tensor(self, name, dtype=torch.float32):
+        call = self._last_call
+        off, nbytes = C.c_size_t(), C.c_size_t()
+        check(_lib.lib().set_editnet_workspace_lookup(C.byref(call.dims), C.byref(call.shape), name.encode(),
+                                                      C.byref(off), C.byref(nbytes)))
+        return call.ws[off.value:off.value + nbytes.value].view(dtype)
+
+
+class DecoderC(EditNetBase):
+    """Drop-in for `DecoderC` of editnet.py:449-548 (cross-entropy stage)."""
+
+    def forward(self, image_features, encoded_captions, caption_lengths, encoded_previous_captions,
+                previous_cap_length, use_ss=False, ss_prob=0.0):
+        pred, call = self._xe(image_features, None, encoded_captions, caption_lengths, encoded_previous_captions,
+                              previous_cap_length, use_ss, ss_prob)
+        return pred, call.caps, call.decode_lengths, call.sort_ind

@@ -1,0 +1,85 @@
+"""Fused train steps for the EditNet path and their data-parallel form.
+
+`XETrainer.step` is the reference's `train()` body (editnet.py:560-581) without autograd:
+forward -> packed cross-entropy (loss + d logits in place) -> reverse pass into one flat
+gradient buffer -> [one NCCL all-reduce of that buffer] -> global-norm clip 0.25 + Adam, all
+of it CUDA kernels from libset_b200.so.  Nothing here synchronises with the host except the
+`.tolist()` on caption lengths that the reference does too (editnet.py:497).
+
+Data parallel (new; the reference has none): one process per GPU, each rank
+holds the full parameters and takes a shard of the batch.  Ranks contribute loss *sums*; the
+flat gradient buffer carries one extra slot holding the rank's token count, so a single
+`all_reduce(SUM)` yields both the summed gradients and the global count, and the optimizer
+kernel divides by it on the device.  The result equals the single-process step on the
+concatenated batch.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr
+from .editnet import _stream
+
+
+class XETrainer:
+    def __init__(self, decoder, lr=5e-4, max_norm=0.25, betas=(0.9, 0.999), eps=1e-8, process_group=None,
+                 distributed=None):
+        self.decoder = decoder
+        self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
+        self.distributed = dist.is_initialized() if distributed is None else distributed
+        self.group = process_group
+        self.step_count = 0
+        self._state = None
+        self.gpu_launches_last_step = 0
+
+    def _ensure_state(self):
+        flat = self.decoder.flatten_parameters()
+        if self._state is None or self._state["flat_ptr"] != flat.data_ptr():
+            n = flat.numel()
+            dev = flat.device
+            # +64: slot n holds the token count that rides along with the gradients
+            self._state = dict(flat_ptr=flat.data_ptr(), n=n,
+                               grad=torch.zeros(n + 64, device=dev), m=torch.zeros(n, device=dev),
+                               v=torch.zeros(n, device=dev), scratch=torch.zeros(8, device=dev),
+                               loss=torch.zeros(2, device=dev))
+        return flat, self._state
+
+    def step(self, image_features, encoded_captions, caption_lengths, encoded_previous_captions,
+             previous_cap_length, image_mean=None, seed=None):
+        """one optimisation step; returns the (device) mean loss of this rank's shard"""
+        dec = self.decoder
+        dec.train()
+        flat, st = self._ensure_state()
+        call = dec._prepare_xe(image_features, image_mean, encoded_captions, caption_lengths,
+                               encoded_previous_captions, previous_cap_length, seed=seed)
+        pred = dec._xe_forward_raw(call)
+        s = call.shape
+        dec_dev = torch.tensor(call.decode_lengths, dtype=torch.int32, device=pred.device)
+        inv = 1.0 if self.distributed else 0.0   # DP: sums, normalised by the global count later
+        check(_lib.lib().set_xe_loss(s.B, s.T, dec.vocab_size, s.Wc, ptr(pred), ptr(call.caps), ptr(dec_dev), inv,
+                                     ptr(st["loss"]), ptr(pred), _stream()))
+        grad = st["grad"]
+        grad.zero_()
+        dec._xe_backward_raw(call, pred, grad[:st["n"]])
+        count_dev = None
+        if self.distributed:
+            grad[st["n"]:st["n"] + 1].copy_(st["loss"][1:2])
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
+            count_dev = grad[st["n"]:st["n"] + 1]
+        self.step_count += 1
+        check(_lib.lib().set_clip_adam(ptr(flat), ptr(grad), ptr(st["m"]), ptr(st["v"]), st["n"], self.step_count,
+                                       self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
+                                       ptr(count_dev), ptr(st["scratch"]), _stream()))
+        self.last_call = call
+        loss = st["loss"][0]
+        if self.distributed:
+            loss = loss / st["loss"][1]
+        return loss
+
+    def grad_norm(self):
+        return self._state["scratch"][1]
+
+    def flat_grad(self):
+        return self._state["grad"][:self._state["n"]]
