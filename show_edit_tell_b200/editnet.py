@@ -249,7 +249,7 @@ class EditNetBase(nn.Module):
                     encoded_previous_captions, previous_cap_length, seed=None):
         self._require_cuda(image_features)
         self.flatten_parameters()
-        lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)        # editnet.py:488
+        lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True, stable=True)  # editnet.py:488 (stable: ties as on CPU)
         call = _Call()
         call.feats = image_features[sort_ind].contiguous().float()
         call.image_mean = None if image_mean is None else image_mean[sort_ind].contiguous().float()

@@ -58,7 +58,9 @@ def compare_grads(mine, ref, tol, label=""):
     bad = []
     for k, r in ref.items():
         m = mine[k].detach().cpu()
-        scale = max(float(r.abs().max()), 1e-6)
+        # floor: gradients that are analytically zero (the bias in front of a softmax) are pure
+        # rounding noise (~1e-10) on both sides
+        scale = max(float(r.abs().max()), 1e-5)
         err = float((m - r).abs().max()) / scale
         if not (err < tol):
             bad.append((k, err, scale))

@@ -83,17 +83,18 @@ def test_golden_xe_eval_forward_backward(tag, small_sd, small_cfg):
     assert not U.compare_grads(U.grads_by_key(mod), ref, GTOL, tag)
 
 
-def _oracle_xe(sd_cpu, batch, masks, adaptive=False):
-    sd = {k: v.clone().requires_grad_(True) for k, v in sd_cpu.items()}
+def _oracle_xe(sd_cpu, batch, masks, adaptive=False, dtype=torch.float32):
+    sd = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd_cpu.items()}
+    im = batch.get("image_mean") if adaptive else None
     preds, caps_sorted, dl, sort_ind, trace = EO.xe_forward(
-        sd, batch["feats"], batch["caps"], batch["caplens"], batch["prev"], batch["prev_len"], masks,
-        image_mean=batch.get("image_mean") if adaptive else None, want_trace=True)
+        sd, batch["feats"].to(dtype), batch["caps"], batch["caplens"], batch["prev"], batch["prev_len"], masks,
+        image_mean=None if im is None else im.to(dtype), want_trace=True)
     loss = EO.xe_loss(preds, caps_sorted, dl)
     import gpu_util
     return preds, loss, gpu_util.oracle_grads(sd, loss), trace
 
 
-def _run_xe_vs_oracle(cfg, sd, batch, train, adaptive=False, seed=1234):
+def _run_xe_vs_oracle(cfg, sd, batch, train, adaptive=False, seed=1234, fp64_truth=False):
     _lib, editnet, editnet_rl, editnet_adaptive, trainmod, U = _imports()
     cls = editnet_adaptive.DecoderC if adaptive else editnet.DecoderC
     mod, _ = U.build_module(cls, sd, cfg["V"], cfg["D"], cfg["A"], cfg["Fdim"])
@@ -131,7 +132,23 @@ def _run_xe_vs_oracle(cfg, sd, batch, train, adaptive=False, seed=1234):
     loss = EO.xe_loss(pred, caps_sorted, dl)
     assert abs(float(loss) - float(ref_loss)) < TOL
     loss.backward()
-    assert not U.compare_grads(U.grads_by_key(mod), ref_grads, GTOL, "train=%s" % train)
+    mine = U.grads_by_key(mod)
+    if not fp64_truth:
+        assert not U.compare_grads(mine, ref_grads, GTOL, "train=%s" % train)
+        return
+    # Ill-conditioned gradients (the visual-attention softmax over near-identical scores cancels to
+    # ~1e-5 of its terms) are noisy in the reference's own fp32 run.  Judge both fp32 paths against
+    # an fp64 run of the oracle: the CUDA path must be within GTOL of the truth or within 5x the
+    # error the reference's fp32 arithmetic itself makes.
+    _, _, truth, _ = _oracle_xe(sd, batch, masks, adaptive, dtype=torch.float64)
+    bad = []
+    for k, r in truth.items():
+        scale = max(float(r.abs().max()), 1e-5)
+        e_m = float((mine[k].cpu().double() - r).abs().max()) / scale
+        e_o = float((ref_grads[k].double() - r).abs().max()) / scale
+        if not e_m < max(GTOL, 5 * e_o):
+            bad.append((k, e_m, e_o))
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("train", [False, True])
@@ -161,7 +178,7 @@ def full_sd():
 def test_full_dims_xe_vs_oracle(train, full_sd):
     c = FULL
     batch = synth.make_batch(c["B"], c["V"], c["R"], c["Fdim"], c["cap_width"], c["prev_width"], ragged=True, seed=21)
-    _run_xe_vs_oracle(c, full_sd, batch, train)
+    _run_xe_vs_oracle(c, full_sd, batch, train, fp64_truth=True)
 
 
 def test_xe_loss_kernel_matches_torch():
@@ -271,14 +288,16 @@ def test_sampling_distribution(small_sd, small_cfg):
         p = F.softmax(F.linear(st[2], sd["fc.weight"], sd["fc.bias"]), dim=1)[0]
     # first sampled token (before the <end>->0 rewrite): recover from seq (0 means <end>)
     tok = seq[:, 0].cpu()
-    tok = torch.where(tok == 0, torch.full_like(tok, V - 1), tok)
     counts = torch.bincount(tok, minlength=V).float()
     expected = p * n
-    chi2 = float(((counts - expected) ** 2 / expected.clamp_min(1e-3)).sum())
+    expected[0] += expected[V - 1]      # <end> is stored as 0 (editnet_rl.py:532): merge the two bins
+    expected[V - 1] = 0
+    raw = mod.workspace_tensor("tok_raw", torch.int64)[:n].cpu()
+    chi2 = float(((counts - expected) ** 2 / expected.clamp_min(1e-3))[:V - 1].sum())
     print("chi2 = %.1f over %d bins" % (chi2, V))
     assert chi2 < 3 * V
     # and the recorded log-prob is the log-prob of the sampled token
-    assert (slp[:, 0].cpu() - torch.log(p)[tok]).abs().max() < 1e-4
+    assert (slp[:, 0].cpu() - torch.log(p)[raw]).abs().max() < 1e-4
 
 
 def test_clip_adam_kernel_matches_oracle():
