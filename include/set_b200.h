@@ -158,6 +158,15 @@ SET_API int set_clip_adam(float* params, const float* grads, float* exp_avg, flo
                   int step, float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,
                   const float* count_dev, float* scratch, void* stream);
 
+/* Number of CUDA kernels this library has launched since the last reset (bench.py reports it). */
+SET_API long long set_launch_count(int reset);
+
+/* Optional timing of the two recurrent loops of the teacher-forced path (CUDA events recorded on
+ * the launch stream around the T forward steps and the T reverse steps of the most recent calls).
+ * set_profile_read() blocks until those events completed; a value of -1 means "not recorded". */
+SET_API int set_profile_enable(int on);
+SET_API int set_profile_read(float* fwd_loop_ms, float* bwd_loop_ms);
+
 /* Test / debugging helpers. */
 /* keep flags (0/1 floats) of dropout site `site` (1 enc-embed, 2 embed, 3 att_embed, 4 fc) for
  * linear element indices [base, base+n) -- the exact bits the kernels use. */

@@ -88,6 +88,9 @@ _P = C.c_void_p
 _SIGS = {
     "set_last_error": (C.c_char_p, []),
     "set_version": (C.c_int, []),
+    "set_launch_count": (C.c_longlong, [C.c_int]),
+    "set_profile_enable": (C.c_int, [C.c_int]),
+    "set_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "set_editnet_workspace_bytes": (C.c_size_t, [C.POINTER(SetDims), C.POINTER(SetSeqShape)]),
     "set_editnet_workspace_lookup": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.c_char_p,
                                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

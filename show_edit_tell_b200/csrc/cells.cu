@@ -561,6 +561,7 @@ __global__ void keep_mask_kernel(float* __restrict__ out, long n, uint64_t seed,
 
 #define LAUNCH_OK()                         \
   SET_CHECK_CUDA(cudaGetLastError());       \
+  set_count_launch(1);                      \
   return SET_OK
 
 }  // namespace

@@ -10,6 +10,7 @@
 #define SET_ERR_WORKSPACE 3
 
 extern "C" void set_record_error(const char* msg);
+extern "C" void set_count_launch(int n);  // bumps the library-wide kernel-launch counter
 
 #define SET_CHECK_CUDA(expr)                                                       \
   do {                                                                             \

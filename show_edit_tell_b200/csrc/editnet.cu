@@ -174,6 +174,19 @@ int make_ctx(Ctx& c, const SetDims* d, const SetSeqShape* s, const SetEditNetPar
   return SET_OK;
 }
 
+// optional timing of the two recurrent loops (bench.py's roofline line): events on the launch stream
+bool g_profile = false;
+cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+int g_ev_state = 0;  // bit0: forward pair recorded, bit1: backward pair recorded
+int profile_mark(int idx, cudaStream_t st) {
+  if (!g_profile) return SET_OK;
+  if (!g_ev[idx]) SET_CHECK_CUDA(cudaEventCreate(&g_ev[idx]));
+  SET_CHECK_CUDA(cudaEventRecord(g_ev[idx], st));
+  if (idx == 1) g_ev_state |= 1;
+  if (idx == 3) g_ev_state |= 2;
+  return SET_OK;
+}
+
 __global__ void fill_kernel(float* p, long n, float v) {
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long)gridDim.x * blockDim.x) p[x] = v;
 }
@@ -192,6 +205,7 @@ int prepare_common(Ctx& c, const float* feats, const float* image_mean_in, const
   SET_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(s.emb_prev), 0, s.regionA_end, st));
   fill_kernel<<<8, 256, 0, st>>>(s.ones, (long)T * B, 1.0f);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   // --- previous-caption encoder
   SET_PROPAGATE(embed_fwd(prev, c.s.Wp, 1, w.embed, c.d.V, s.emb_prev, P, B, D, c.s.train, c.seed, kSiteEnc, 0, 1,
                           c.s.Wp, st));
@@ -392,6 +406,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     p.a_inner = dl.inner; p.a_ld_inner = dl.ld_inner; p.a_row_len = dl.row_len; p.a_valid_inner = B;
     SET_PROPAGATE(gemm(kNN, p, st));
   }
+  SET_PROPAGATE(profile_mark(2, st));
   for (int t = T - 1; t >= 0; --t) {
     const int b = bt_host[t];
     if (b <= 0) continue;
@@ -459,6 +474,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       SET_PROPAGATE(gemm_group(kNN, p, 2, st));
     }
   }
+  SET_PROPAGATE(profile_mark(3, st));
   // ---- time-batched tail: input gradients
   SET_PROPAGATE(sum_time(s.dG1, s.sumG1, T, (long)B * 4 * D, st));
   {
@@ -828,7 +844,9 @@ int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const 
   SET_PROPAGATE(embed_fwd(caps, shape->Wc, 1, w->embed, V, c.ws.emb_all, T, B, D, shape->train, seed, kSiteEmb, 0, B, 1,
                           c.st));
   SET_PROPAGATE(project_words(c, 0, T));
+  SET_PROPAGATE(profile_mark(0, c.st));
   for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
+  SET_PROPAGATE(profile_mark(1, c.st));
   // vocabulary projection for all decoded rows at once (editnet.py:545-546), written batch-major
   SET_CHECK_CUDA(cudaMemsetAsync(predictions, 0, sizeof(float) * (size_t)B * T * V, c.st));
   GemmProblem p = gemm_problem(T * B, V, predictions, V);
@@ -864,8 +882,10 @@ int set_xe_loss(int B, int T, int V, int Wc, const float* predictions, const int
   xe_loss_kernel<<<B * T, 256, 0, st>>>(B, T, V, Wc, predictions, caps, decode_len_dev, inv_count, loss_out,
                                         d_predictions);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   xe_count_kernel<<<1, 32, 0, st>>>(B, T, decode_len_dev, loss_out);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   return SET_OK;
 }
 
@@ -885,6 +905,7 @@ int set_editnet_rollout(const SetDims* dims, const SetSeqShape* shape, const Set
   SET_CHECK_CUDA(cudaMemsetAsync(seq_logprobs, 0, sizeof(float) * (size_t)B * T, c.st));
   fill_i64_kernel<<<1, 256, 0, c.st>>>(s.it, B, start_token);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   for (int t = 0; t < T; ++t) {
     SET_PROPAGATE(embed_fwd(s.it + (size_t)t * B, 1, 0, w->embed, V, s.emb_all + (size_t)t * B * D, 1, B, D,
                             shape->train, seed, kSiteEmb, (long)t * B, 0, 1, c.st));
@@ -898,6 +919,7 @@ int set_editnet_rollout(const SetDims* dims, const SetSeqShape* shape, const Set
     sample_step_kernel<<<B, 256, 0, c.st>>>(lg, V, B, T, t, mode, forced, seed, end_token, s.unfinished,
                                             s.unf_count, s.it + (size_t)(t + 1) * B, seq, seq_logprobs, s.lse, s.tok_raw);
     SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   }
   return SET_OK;
 }
@@ -914,6 +936,7 @@ int set_editnet_rollout_backward(const SetDims* dims, const SetSeqShape* shape, 
   Ws& s = c.ws;
   rollout_dlogits_kernel<<<T * B, 256, 0, c.st>>>(s.logits, V, B, T, d_seq_logprobs, s.lse, s.tok_raw);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   std::vector<int> bt(T, B);
   DLogits dl;
   dl.p = s.logits; dl.ld = V; dl.inner = 0; dl.ld_inner = 0; dl.row_len = nullptr;
@@ -928,6 +951,27 @@ int set_reward_criterion(int B, int T, const float* seq_logprobs, const int64_t*
   reward_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(B, T, seq_logprobs, seq, reward, loss_out,
                                                                        d_logprobs);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
+  return SET_OK;
+}
+
+int set_profile_enable(int on) {
+  g_profile = on != 0;
+  g_ev_state = 0;
+  return SET_OK;
+}
+
+int set_profile_read(float* fwd_loop_ms, float* bwd_loop_ms) {
+  if (fwd_loop_ms) *fwd_loop_ms = -1.f;
+  if (bwd_loop_ms) *bwd_loop_ms = -1.f;
+  if ((g_ev_state & 1) && fwd_loop_ms) {
+    SET_CHECK_CUDA(cudaEventSynchronize(g_ev[1]));
+    SET_CHECK_CUDA(cudaEventElapsedTime(fwd_loop_ms, g_ev[0], g_ev[1]));
+  }
+  if ((g_ev_state & 2) && bwd_loop_ms) {
+    SET_CHECK_CUDA(cudaEventSynchronize(g_ev[3]));
+    SET_CHECK_CUDA(cudaEventElapsedTime(bwd_loop_ms, g_ev[2], g_ev[3]));
+  }
   return SET_OK;
 }
 

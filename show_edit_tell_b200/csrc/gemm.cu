@@ -183,6 +183,7 @@ template <int MODE, int BN>
 int launch(const GemmGroup& g, int total_tiles, cudaStream_t stream) {
   gemm_kernel<MODE, BN><<<total_tiles, 256, 0, stream>>>(g);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   return SET_OK;
 }
 
@@ -250,6 +251,7 @@ int colsum(const float* X, long ld, int M, int N, float* out, int beta, cudaStre
   if (gy > 64) gy = 64;
   colsum_kernel<<<dim3((N + 31) / 32, gy), block, 0, stream>>>(X, ld, M, N, out);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   return SET_OK;
 }
 

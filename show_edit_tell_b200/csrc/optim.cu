@@ -1,5 +1,6 @@
 // Error reporting, version, and the fused optimizer tail of the train step:
 // global-norm clip + Adam over one flat buffer (train() tail, editnet.py:580-581).
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -24,6 +25,14 @@ extern "C" const char* set_last_error(void) {
 }
 
 extern "C" int set_version(void) { return 100; }
+
+namespace {
+std::atomic<long long> g_launches{0};
+}
+extern "C" void set_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long set_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
 
 namespace set {
 namespace {
@@ -81,10 +90,12 @@ extern "C" int set_clip_adam(float* params, const float* grads, float* exp_avg, 
   const int blocks = 148 * 8;
   set::sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, scratch);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   set::adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2s,
                                            max_norm, grad_scale, count_dev, scratch);
   SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
   return SET_OK;
 }
