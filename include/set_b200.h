@@ -97,7 +97,9 @@ SET_API size_t set_editnet_workspace_bytes(const SetDims* dims, const SetSeqShap
  *   caps             [B,Wc]    encoded_captions[sort_ind] (int64)
  *   decode_len_host  [B]       HOST ints, caption_lengths-1, non-increasing (editnet.py:497)
  *   prev, prev_len   [B,Wp],[B] encoded_previous_captions / previous_cap_length, sorted rows (int64)
- *   predictions      [B,T,V]   written in full: rows t >= decode_len[i] are zero (editnet.py:499,546)
+ *   predictions      [B,T,V]   written in full: rows t >= decode_len[i] are zero (editnet.py:499,546);
+ *                              NULL (train mode only): the logits stay time-major [T,B,V] inside the
+ *                              workspace for set_editnet_xe_loss_time_major / backward(d_predictions=NULL)
  * The workspace keeps what set_editnet_xe_backward needs; it must stay untouched between
  * the two calls. */
 SET_API int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
@@ -109,7 +111,8 @@ SET_API int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape
 /* Backward of the above for an upstream gradient d_predictions [B,T,V] (entries at
  * t >= decode_len[i] are ignored, as the reference's slice-assignment does).  Replaces the
  * autograd replay that `loss.backward()` (editnet.py:579) performs through DecoderC.forward.
- * Gradients are ACCUMULATED into *grads. */
+ * d_predictions == NULL takes d(logits) from the workspace (written there by
+ * set_editnet_xe_loss_time_major).  Gradients are ACCUMULATED into *grads. */
 SET_API int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
                             const SetEditNetParams* grads, const float* feats, const int64_t* caps,
                             const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
@@ -124,6 +127,12 @@ SET_API int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shap
 SET_API int set_xe_loss(int B, int T, int V, int Wc, const float* predictions, const int64_t* caps,
                 const int* decode_len_dev, float inv_count, float* loss_out, float* d_predictions,
                 void* stream);
+
+/* Same loss on the time-major logits a set_editnet_xe_forward(predictions=NULL) call left in the
+ * workspace; overwrites them with d(loss)/d(logits).  loss_out as above. */
+SET_API int set_editnet_xe_loss_time_major(const SetDims* dims, const SetSeqShape* shape, const int64_t* caps,
+                                   float inv_count, float* loss_out, void* workspace, size_t workspace_bytes,
+                                   void* stream);
 
 /* Autoregressive rollout: replaces DecoderC.forward of editnet_rl.py:485-549.
  *   mode 0 = greedy (sample_max, :521), 1 = multinomial sample (sample_rl, :525-527; inverse-CDF
@@ -174,6 +183,11 @@ SET_API int set_dropout_keep_mask(float* out, size_t n, uint64_t seed, int site,
 /* byte offset and byte size of a named workspace buffer for this shape (returns 0 if found). */
 SET_API int set_editnet_workspace_lookup(const SetDims* dims, const SetSeqShape* shape, const char* name,
                                  size_t* offset, size_t* bytes);
+/* GEMM engine selection: 0 = tcgen05 3xTF32 tensor-core kernel where a problem is eligible (16-byte
+ * aligned operands, K >= 64), CUDA-core fp32 kernel otherwise; 1 = CUDA-core kernel only.  Both are
+ * this library's own kernels; the switch exists for A/B parity tests and profiling. */
+SET_API int set_gemm_backend(int backend);
+SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
 /* C = A @ B^T style contraction through the library's GEMM engine (mode 0 NT, 1 NN, 2 TN). */
 SET_API int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,
              const float* bias, float* C, long ldc, int beta, int act, void* stream);

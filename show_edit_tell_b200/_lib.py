@@ -100,6 +100,8 @@ _SIGS = {
                                           C.POINTER(SetEditNetParams), _P, _P, C.POINTER(C.c_int), _P, _P,
                                           C.c_uint64, _P, _P, C.c_size_t, _P]),
     "set_xe_loss": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, _P, _P]),
+    "set_editnet_xe_loss_time_major": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), _P, C.c_float, _P, _P,
+                                                 C.c_size_t, _P]),
     "set_editnet_rollout": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),
                                       _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, C.c_uint64, _P, _P, _P,
                                       C.c_size_t, _P]),
@@ -110,6 +112,8 @@ _SIGS = {
     "set_clip_adam": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _P, _P, _P]),
     "set_dropout_keep_mask": (C.c_int, [_P, C.c_size_t, C.c_uint64, C.c_int, C.c_size_t, _P]),
+    "set_gemm_backend": (C.c_int, [C.c_int]),
+    "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_long, _P, C.c_long, _P, _P, C.c_long,
                            C.c_int, C.c_int, _P]),
 }

@@ -547,6 +547,20 @@ __global__ void dropout_fwd_kernel(const float* __restrict__ x, float* __restric
     out[y] = v;
   }
 }
+__global__ void transpose_kernel(const float* __restrict__ in, long ld_in, float* __restrict__ out, long ld_out,
+                                 int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(long)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(long)c * ld_out + r] = tile[threadIdx.x][j];
+  }
+}
 __global__ void sum_time_kernel(const float* __restrict__ x, float* __restrict__ out, int T, long n) {
   for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < n; y += (long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -712,6 +726,16 @@ int dropout_fwd(const float* x, float* out, int rows, int D, int train, uint64_t
   const long n = (long)rows * D;
   if (n <= 0) return SET_OK;
   dropout_fwd_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(x, out, n, train, seed, site, drop_base);
+  LAUNCH_OK();
+}
+int transpose(const float* in, float* out, int rows, int cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return SET_OK;
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(in, cols, out, rows, rows, cols);
+  LAUNCH_OK();
+}
+int transpose_ld(const float* in, long ld_in, float* out, long ld_out, int rows, int cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return SET_OK;
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(in, ld_in, out, ld_out, rows, cols);
   LAUNCH_OK();
 }
 int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s) {

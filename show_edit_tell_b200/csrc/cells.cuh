@@ -125,6 +125,10 @@ int copy1_bwd(const float* dcnew, const float* g2, const float* c2_prev, float* 
 int dropout_fwd(const float* x, float* out, int rows, int D, int train, uint64_t seed, uint32_t site,
                 long drop_base, cudaStream_t s);
 
+// out[c][r] = in[r][c]   (in is [rows][cols], dense)
+int transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);
+// strided form: out[c*ld_out + r] = in[r*ld_in + c]
+int transpose_ld(const float* in, long ld_in, float* out, long ld_out, int rows, int cols, cudaStream_t s);
 // sum over time of a [T][B][N] buffer -> [B][N]
 int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s);
 // materialise keep bits as floats (tests): out[i] = keep(seed, site, base+i)

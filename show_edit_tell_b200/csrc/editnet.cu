@@ -50,7 +50,11 @@ struct Ws {
   float *dG1, *dS2, *dG2, *dsc, *dK, *dh2raw, *datt1, *datt1c, *dprev_h, *dprev_m, *dfh, *dfe_pre, *dfe_t;
   float *demb_all, *demb_prev, *denc_g, *dh_last, *dh_run, *dc_run, *sumG1;
   float *dh2c, *dc2c, *dh1c, *dc1c, *dX2, *dctx, *dsel, *dcnew;
-  size_t regionA_end = 0, regionB_begin = 0, total = 0;
+  // ---- transposed weight copies for the dX pass (written at the start of backward, never zeroed)
+  float *t_fc, *t_cl_gcn, *t_cl_gcm, *t_cl_x2h, *t_ca_gate, *t_ca_sc, *t_ca_dec, *t_va_dec, *t_ca_tc, *t_al_whh,
+      *t_al_wih, *t_cl_h2h, *t_ca_feat, *t_va_feat, *t_enc_aff, *t_enc_h2h, *t_enc_x2h;
+  float* tscratch; size_t tscratch_floats;   // transposed activations for the dW pass
+  size_t regionA_end = 0, regionB_begin = 0, regionB_end = 0, total = 0;
 };
 
 struct Ctx {
@@ -142,6 +146,32 @@ void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
   w.dctx = ar.take<float>("dctx", B * D);
   w.dsel = ar.take<float>("dsel", B * D);
   w.dcnew = ar.take<float>("dcnew", B * D);
+  w.regionB_end = ar.off;
+  w.t_fc = ar.take<float>("t_fc", V * D);
+  w.t_cl_gcn = ar.take<float>("t_cl_gcn", D * D);
+  w.t_cl_gcm = ar.take<float>("t_cl_gcm", D * D);
+  w.t_cl_x2h = ar.take<float>("t_cl_x2h", 4 * D * (2 * D + F));
+  w.t_ca_gate = ar.take<float>("t_ca_gate", D * 3 * D);
+  w.t_ca_sc = ar.take<float>("t_ca_sc", D * D);
+  w.t_ca_dec = ar.take<float>("t_ca_dec", A * D);
+  w.t_va_dec = ar.take<float>("t_va_dec", A * D);
+  w.t_ca_tc = ar.take<float>("t_ca_tc", D * 2 * D);
+  w.t_al_whh = ar.take<float>("t_al_whh", 4 * D * D);
+  w.t_al_wih = ar.take<float>("t_al_wih", 4 * D * (3 * D + F));
+  w.t_cl_h2h = ar.take<float>("t_cl_h2h", 4 * D * D);
+  w.t_ca_feat = ar.take<float>("t_ca_feat", A * D);
+  w.t_va_feat = ar.take<float>("t_va_feat", A * D);
+  w.t_enc_aff = ar.take<float>("t_enc_aff", D * D);
+  w.t_enc_h2h = ar.take<float>("t_enc_h2h", 4 * D * D);
+  w.t_enc_x2h = ar.take<float>("t_enc_x2h", 4 * D * D);
+  {
+    // upper bound of everything backward_core transposes for the dW pass (rows padded to 4)
+    const size_t TB = T * B + 4, BRr = B * R + 4, TBR = (s.train ? T : 1) * B * R + 4, BP = B * P + 4, PB = P * B + 4;
+    w.tscratch_floats = TB * (4 * D + D + D + (2 * D + F) + 4 * D + (2 * A + 2 * D) + 5 * D + V + D) +
+                        (B + 4) * (4 * D + D + F + 2 * D) + BP * (A + D) + TBR * (A + D) + BRr * (D + F) +
+                        PB * (4 * D + 2 * D) + 4096;
+    w.tscratch = ar.take<float>("tscratch", w.tscratch_floats);
+  }
   w.total = ar.off;
 }
 
@@ -391,7 +421,8 @@ struct DLogits {
 };
 
 int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const int64_t* caps_tok, long tok_ld,
-                  long tok_os, const int64_t* prev, const int64_t* prev_len, const int* bt_host, DLogits dl) {
+                  long tok_os, const int64_t* prev, const int64_t* prev_len, const int* bt_host, DLogits dl,
+                  const int* dec_len_dev) {
   const int B = c.s.B, P = c.s.P, T = c.s.T, R = c.s.R, D = c.d.D, A = c.d.A, F = c.d.F, V = c.d.V;
   const int LS2 = c.LS2, LX2 = c.LX2;
   const SetEditNetParams& w = *c.w;
@@ -399,12 +430,33 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   cudaStream_t st = c.st;
   const int TB = T * B;
   SET_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(s.emb_prev) + s.regionB_begin, 0,
-                                 s.total - s.regionB_begin, st));
+                                 s.regionB_end - s.regionB_begin, st));
+  // The dX pass contracts over a weight's OUTPUT features.  The tensor-core kernel wants both operands
+  // with the same major-ness (mixed K-major x MN-major tf32 operands read back as zeros on sm_100a), so
+  // when it is enabled each weight gets a transposed copy W^T [in][out] and dX = dY @ W becomes the NT
+  // form dY @ (W^T)^T.  ~0.3 GB of traffic per train step; the CUDA-core path reads W in place (NN).
+  const bool use_wt = (g_backend == 0);
+  const int dxm = use_wt ? kNT : kNN;
+  if (use_wt) {
+    struct { const float* w; float* t; int O, I; } tr[] = {
+        {w.fc_w, s.t_fc, V, D}, {w.cl_gcn_w, s.t_cl_gcn, D, D}, {w.cl_gcm_w, s.t_cl_gcm, D, D},
+        {w.cl_x2h_w, s.t_cl_x2h, 4 * D, LX2}, {w.ca_gate_w, s.t_ca_gate, D, 3 * D}, {w.ca_sc_w, s.t_ca_sc, D, D},
+        {w.ca_dec_w, s.t_ca_dec, A, D}, {w.va_dec_w, s.t_va_dec, A, D}, {w.ca_tc_w, s.t_ca_tc, D, 2 * D},
+        {w.al_whh, s.t_al_whh, 4 * D, D}, {w.al_wih, s.t_al_wih, 4 * D, 3 * D + F}, {w.cl_h2h_w, s.t_cl_h2h, 4 * D, D},
+        {w.ca_feat_w, s.t_ca_feat, A, D}, {w.va_feat_w, s.t_va_feat, A, D}, {w.enc_aff_w, s.t_enc_aff, D, D},
+        {w.enc_h2h_w, s.t_enc_h2h, 4 * D, D}, {w.enc_x2h_w, s.t_enc_x2h, 4 * D, D}};
+    for (auto& e : tr) SET_PROPAGATE(transpose(e.w, e.t, e.O, e.I, st));
+  }
+  // one dX term: out[m][j] += sum_o dY[m][o] * W[o][c0 + j]   (W is [O][I])
+  auto dx = [&](GemmProblem& p, const float* dY, long ldy, const float* W, const float* WTp, int O, int I, int c0) {
+    if (use_wt) gemm_add_seg(p, dY, ldy, WTp + (size_t)c0 * O, O, O);
+    else gemm_add_seg(p, dY, ldy, W + c0, I, O);
+  };
   {  // d(dropout(h2)) for every step at once: dlogits @ fc.weight
     GemmProblem p = gemm_problem(TB, D, s.dh2raw, D);
-    gemm_add_seg(p, dl.p, dl.ld, w.fc_w, D, V);
+    dx(p, dl.p, dl.ld, w.fc_w, s.t_fc, V, D, 0);
     p.a_inner = dl.inner; p.a_ld_inner = dl.ld_inner; p.a_row_len = dl.row_len; p.a_valid_inner = B;
-    SET_PROPAGATE(gemm(kNN, p, st));
+    SET_PROPAGATE(gemm(dxm, p, st));
   }
   SET_PROPAGATE(profile_mark(2, st));
   for (int t = T - 1; t >= 0; --t) {
@@ -421,23 +473,23 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
                             (long)tb * D, st));
     {
       GemmProblem p[2];
-      p[0] = gemm_problem(b, D, s.dcnew, D); gemm_add_seg(p[0], dKt, D, w.cl_gcn_w, D, D); p[0].beta = 1;
-      p[1] = gemm_problem(b, D, s.dsel, D); gemm_add_seg(p[1], dKt, D, w.cl_gcm_w, D, D); p[1].beta = 1;
-      SET_PROPAGATE(gemm_group(kNN, p, 2, st));
+      p[0] = gemm_problem(b, D, s.dcnew, D); dx(p[0], dKt, D, w.cl_gcn_w, s.t_cl_gcn, D, D, 0); p[0].beta = 1;
+      p[1] = gemm_problem(b, D, s.dsel, D); dx(p[1], dKt, D, w.cl_gcm_w, s.t_cl_gcm, D, D, 0); p[1].beta = 1;
+      SET_PROPAGATE(gemm_group(dxm, p, 2, st));
     }
     SET_PROPAGATE(copy1_bwd(s.dcnew, g2t, s.c2 + tb * D, dG2t, s.dc2c, b, D, st));
     {
       GemmProblem p = gemm_problem(b, LX2, s.dX2, LX2);      // d[h1 | att_cap | att_img]
-      gemm_add_seg(p, dG2t, 4 * D, w.cl_x2h_w, LX2, 4 * D);
-      SET_PROPAGATE(gemm(kNN, p, st));
+      dx(p, dG2t, 4 * D, w.cl_x2h_w, s.t_cl_x2h, 4 * D, LX2, 0);
+      SET_PROPAGATE(gemm(dxm, p, st));
     }
     SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, s.dX2 + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
                                s.dsc + tb * D, b, D, st));
     {
       GemmProblem p = gemm_problem(b, D, s.dctx, D);
-      gemm_add_seg(p, dS2t + 2 * A, LS2, w.ca_gate_w + 2 * D, 3 * D, D);
-      gemm_add_seg(p, s.dsc + tb * D, D, w.ca_sc_w, D, D);
-      SET_PROPAGATE(gemm(kNN, p, st));
+      dx(p, dS2t + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, 2 * D);
+      dx(p, s.dsc + tb * D, D, w.ca_sc_w, s.t_ca_sc, D, D, 0);
+      SET_PROPAGATE(gemm(dxm, p, st));
     }
     {
       AttnBwdArgs a;
@@ -456,22 +508,22 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     }
     {
       GemmProblem p = gemm_problem(b, D, s.dX2, LX2);        // dh1 += every consumer of h1
-      gemm_add_seg(p, dS2t, LS2, w.ca_dec_w, D, A);
-      gemm_add_seg(p, dS2t + A, LS2, w.va_dec_w, D, A);
-      gemm_add_seg(p, dS2t + 2 * A, LS2, w.ca_gate_w + D, 3 * D, D);
-      gemm_add_seg(p, dS2t + 2 * A + D, LS2, w.ca_tc_w + D, 2 * D, D);
+      dx(p, dS2t, LS2, w.ca_dec_w, s.t_ca_dec, A, D, 0);
+      dx(p, dS2t + A, LS2, w.va_dec_w, s.t_va_dec, A, D, 0);
+      dx(p, dS2t + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, D);
+      dx(p, dS2t + 2 * A + D, LS2, w.ca_tc_w, s.t_ca_tc, D, 2 * D, D);
       p.beta = 1;
-      SET_PROPAGATE(gemm(kNN, p, st));
+      SET_PROPAGATE(gemm(dxm, p, st));
     }
     SET_PROPAGATE(lstm_bwd(s.gates1 + tb * 4 * D, s.c1 + tb * D, s.c1 + (tb + B) * D, s.dX2, LX2, s.dh1c, s.dc1c,
                            dG1t, b, D, st));
     if (t > 0) {
       GemmProblem p[2];
-      p[0] = gemm_problem(b, D, s.dh1c, D); gemm_add_seg(p[0], dG1t, 4 * D, w.al_whh, D, 4 * D);
+      p[0] = gemm_problem(b, D, s.dh1c, D); dx(p[0], dG1t, 4 * D, w.al_whh, s.t_al_whh, 4 * D, D, 0);
       p[1] = gemm_problem(b, D, s.dh2c, D);
-      gemm_add_seg(p[1], dG1t, 4 * D, w.al_wih + 2 * D, 3 * D + F, 4 * D);
-      gemm_add_seg(p[1], dG2t, 4 * D, w.cl_h2h_w, D, 4 * D);
-      SET_PROPAGATE(gemm_group(kNN, p, 2, st));
+      dx(p[1], dG1t, 4 * D, w.al_wih, s.t_al_wih, 4 * D, 3 * D + F, 2 * D);
+      dx(p[1], dG2t, 4 * D, w.cl_h2h_w, s.t_cl_h2h, 4 * D, D, 0);
+      SET_PROPAGATE(gemm_group(dxm, p, 2, st));
     }
   }
   SET_PROPAGATE(profile_mark(3, st));
@@ -480,19 +532,44 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   {
     GemmProblem p[2];
     p[0] = gemm_problem(B, D, s.dfh, D);                      // d final_hidden
-    gemm_add_seg(p[0], s.sumG1, 4 * D, w.al_wih + D, 3 * D + F, 4 * D);
+    dx(p[0], s.sumG1, 4 * D, w.al_wih, s.t_al_wih, 4 * D, 3 * D + F, D);
     p[1] = gemm_problem(TB, D, s.demb_all, D);                // d embeddings (three consumers)
-    gemm_add_seg(p[1], s.dG1, 4 * D, w.al_wih, 3 * D + F, 4 * D);
-    gemm_add_seg(p[1], s.dS2 + 2 * A, LS2, w.ca_gate_w, 3 * D, D);
-    gemm_add_seg(p[1], s.dS2 + 2 * A + D, LS2, w.ca_tc_w, 2 * D, D);
-    SET_PROPAGATE(gemm_group(kNN, p, 2, st));
+    dx(p[1], s.dG1, 4 * D, w.al_wih, s.t_al_wih, 4 * D, 3 * D + F, 0);
+    dx(p[1], s.dS2 + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, 0);
+    dx(p[1], s.dS2 + 2 * A + D, LS2, w.ca_tc_w, s.t_ca_tc, D, 2 * D, 0);
+    SET_PROPAGATE(gemm_group(dxm, p, 2, st));
   }
   SET_PROPAGATE(embed_bwd(caps_tok, tok_ld, tok_os, s.emb_all, s.demb_all, g.embed, V, T, B, D, c.s.train,
-                          dl.row_len, st));
+                          dec_len_dev, st));
   // ---- time-batched tail: weight gradients (dY^T X over all T*B rows; undecoded rows are zero)
+  // With the tensor-core engine dW = dY^T X is issued in NT form on explicit transposes of the two
+  // activation matrices (K-major operands only, see the note on W^T above); each distinct matrix is
+  // transposed once per backward call into `tscratch`.
+  struct TrEntry { const float* src; long ld; int rows, cols; const float* dst; };
+  std::vector<TrEntry> tr_cache;
+  size_t tr_used = 0;
+  int tr_err = SET_OK;
+  auto TR = [&](const float* X, long ld, int rows, int cols) -> const float* {
+    for (const auto& e : tr_cache)
+      if (e.src == X && e.ld == ld && e.rows == rows && e.cols == cols) return e.dst;
+    const size_t rp = ((size_t)rows + 3) & ~size_t(3);
+    if (tr_used + rp * cols > s.tscratch_floats) { tr_err = SET_ERR_WORKSPACE; return nullptr; }
+    float* dst = s.tscratch + tr_used;
+    tr_used += rp * cols;
+    const int r = transpose_ld(X, ld, dst, (long)rp, rows, cols, st);
+    if (r != SET_OK) tr_err = r;
+    tr_cache.push_back({X, ld, rows, cols, dst});
+    return dst;
+  };
+  const int dwm = use_wt ? kNT : kTN;
   auto TN = [&](float* C, long ldc, int M, int N, const float* dY, long ldy, const float* X, long ldx, int K) {
     GemmProblem p = gemm_problem(M, N, C, ldc);
-    gemm_add_seg(p, dY, ldy, X, ldx, K);
+    if (use_wt) {
+      const long rp = ((long)K + 3) & ~3L;
+      gemm_add_seg(p, TR(dY, ldy, K, M), rp, TR(X, ldx, K, N), rp, K);
+    } else {
+      gemm_add_seg(p, dY, ldy, X, ldx, K);
+    }
     p.beta = 1;
     return p;
   };
@@ -506,7 +583,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     p[n++] = TN(g.al_wih + 3 * D, 3 * D + F, 4 * D, F, s.sumG1, 4 * D, s.image_mean, F, B);
     p[n++] = TN(g.cl_x2h_w, LX2, 4 * D, LX2, s.dG2, 4 * D, s.X2, LX2, TB);
     p[n++] = TN(g.cl_h2h_w, D, 4 * D, D, s.dG2, 4 * D, s.h2, D, TB);
-    SET_PROPAGATE(gemm_group(kTN, p, n, st));
+    SET_PROPAGATE(gemm_group(dwm, p, n, st));
   }
   {
     GemmProblem p[8];
@@ -519,7 +596,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     p[n++] = TN(g.ca_sc_w, D, D, D, s.dsc, D, s.ctx_c, D, TB);
     p[n++] = TN(g.ca_tc_w, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.emb_all, D, TB);
     p[n++] = TN(g.ca_tc_w + D, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.X2, LX2, TB);
-    SET_PROPAGATE(gemm_group(kTN, p, n, st));
+    SET_PROPAGATE(gemm_group(dwm, p, n, st));
   }
   {
     GemmProblem p[8];
@@ -527,13 +604,23 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     p[n++] = TN(g.cl_gcn_w, D, D, D, s.dK, D, s.cnew, D, TB);
     p[n++] = TN(g.cl_gcm_w, D, D, D, s.dK, D, s.sel, D, TB);
     p[n++] = TN(g.ca_feat_w, D, A, D, s.datt1c, A, s.prev_h, D, B * P);
-    p[n] = TN(g.fc_w, D, V, D, dl.p, dl.ld, s.h2drop, D, TB);
-    p[n].a_inner = dl.inner; p[n].a_ld_inner = dl.ld_inner; p[n].a_row_len = dl.row_len; p[n].a_valid_inner = B;
-    ++n;
-    p[n] = TN(g.fc_b, 1, V, 1, dl.p, dl.ld, s.ones, 1, TB);
-    p[n].a_inner = dl.inner; p[n].a_ld_inner = dl.ld_inner; p[n].a_row_len = dl.row_len; p[n].a_valid_inner = B;
-    ++n;
-    SET_PROPAGATE(gemm_group(kTN, p, n, st));
+    const bool dl_plain = (dl.inner == 0 && dl.row_len == nullptr);   // time-major d logits (trainer / rollout)
+    if (dl_plain) p[n++] = TN(g.fc_w, D, V, D, dl.p, dl.ld, s.h2drop, D, TB);
+    SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
+    SET_PROPAGATE(gemm_group(dwm, p, n, st));
+    if (dl_plain) {
+      SET_PROPAGATE(colsum(dl.p, dl.ld, TB, V, g.fc_b, 1, st));
+    } else {
+      // batch-major upstream gradient (autograd drop-in path): strided, masked rows -> CUDA-core TN kernel
+      GemmProblem q[2];
+      for (int k = 0; k < 2; ++k) {
+        q[k] = k == 0 ? gemm_problem(V, D, g.fc_w, D) : gemm_problem(V, 1, g.fc_b, 1);
+        gemm_add_seg(q[k], dl.p, dl.ld, k == 0 ? s.h2drop : s.ones, k == 0 ? D : 1, TB);
+        q[k].beta = 1;
+        q[k].a_inner = dl.inner; q[k].a_ld_inner = dl.ld_inner; q[k].a_row_len = dl.row_len; q[k].a_valid_inner = B;
+      }
+      SET_PROPAGATE(gemm_group(kTN, q, 2, st));
+    }
   }
   SET_PROPAGATE(colsum(s.dG1, 4 * D, TB, 4 * D, g.al_bih, 1, st));
   SET_PROPAGATE(colsum(s.dG1, 4 * D, TB, 4 * D, g.al_bhh, 1, st));
@@ -549,43 +636,43 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   SET_PROPAGATE(colsum(s.datt1c, A, B * P, A, g.ca_feat_b, 1, st));
   {  // d prev_h also flows through cap_features_att
     GemmProblem p = gemm_problem(B * P, D, s.dprev_h, D);
-    gemm_add_seg(p, s.datt1c, A, w.ca_feat_w, D, A);
+    dx(p, s.datt1c, A, w.ca_feat_w, s.t_ca_feat, A, D, 0);
     p.beta = 1;
-    SET_PROPAGATE(gemm(kNN, p, st));
+    SET_PROPAGATE(gemm(dxm, p, st));
   }
   // ---- visual feature path
   if (c.s.train) {
     const int TBR = T * B * R;
     GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_t, D, TBR);
-    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.datt1, A, TBR, A, g.va_feat_b, 1, st));
     GemmProblem px = gemm_problem(TBR, D, s.dfe_t, D);
-    gemm_add_seg(px, s.datt1, A, w.va_feat_w, D, A);
-    SET_PROPAGATE(gemm(kNN, px, st));
-    SET_PROPAGATE(vis_dropout_bwd(s.fe_pre, s.dfe_t, s.dfe_pre, dl.row_len, T, B, R, D, c.seed, st));
+    dx(px, s.datt1, A, w.va_feat_w, s.t_va_feat, A, D, 0);
+    SET_PROPAGATE(gemm(dxm, px, st));
+    SET_PROPAGATE(vis_dropout_bwd(s.fe_pre, s.dfe_t, s.dfe_pre, dec_len_dev, T, B, R, D, c.seed, st));
   } else {
     GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_pre, D, B * R);
-    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.datt1, A, B * R, A, g.va_feat_b, 1, st));
     GemmProblem px = gemm_problem(B * R, D, s.dfe_pre, D);
-    gemm_add_seg(px, s.datt1, A, w.va_feat_w, D, A);
-    SET_PROPAGATE(gemm(kNN, px, st));
+    dx(px, s.datt1, A, w.va_feat_w, s.t_va_feat, A, D, 0);
+    SET_PROPAGATE(gemm(dxm, px, st));
     SET_PROPAGATE(relu_bwd_inplace(s.dfe_pre, s.fe_pre, (long)B * R * D, st));
   }
   {
     GemmProblem pw = TN(g.va_emb_w, F, D, F, s.dfe_pre, D, feats, F, B * R);
-    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.dfe_pre, D, B * R, D, g.va_emb_b, 1, st));
   }
   // ---- caption encoder BPTT (reverse of editnet.py:333-341)
   SET_PROPAGATE(tanh_bwd_inplace(s.dfh, s.fh, (long)B * D, st));
   {
     GemmProblem pw = TN(g.enc_aff_w, D, D, D, s.dfh, D, s.enc_h + (size_t)P * B * D, D, B);
-    SET_PROPAGATE(gemm(kTN, pw, st));
+    SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.dfh, D, B, D, g.enc_aff_b, 1, st));
     GemmProblem px = gemm_problem(B, D, s.dh_last, D);
-    gemm_add_seg(px, s.dfh, D, w.enc_aff_w, D, D);
-    SET_PROPAGATE(gemm(kNN, px, st));
+    dx(px, s.dfh, D, w.enc_aff_w, s.t_enc_aff, D, D, 0);
+    SET_PROPAGATE(gemm(dxm, px, st));
   }
   for (int t = P - 1; t >= 0; --t) {
     const size_t tb = (size_t)t * B;
@@ -594,22 +681,23 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
                                s.denc_g + tb * 4 * D, B, D, st));
     if (t > 0) {
       GemmProblem p = gemm_problem(B, D, s.dh_run, D);
-      gemm_add_seg(p, s.denc_g + tb * 4 * D, 4 * D, w.enc_h2h_w, D, 4 * D);
-      SET_PROPAGATE(gemm(kNN, p, st));
+      dx(p, s.denc_g + tb * 4 * D, 4 * D, w.enc_h2h_w, s.t_enc_h2h, 4 * D, D, 0);
+      SET_PROPAGATE(gemm(dxm, p, st));
     }
   }
   {
     GemmProblem p[2];
     p[0] = TN(g.enc_x2h_w, D, 4 * D, D, s.denc_g, 4 * D, s.emb_prev, D, P * B);
     p[1] = TN(g.enc_h2h_w, D, 4 * D, D, s.denc_g, 4 * D, s.enc_h, D, P * B);
-    SET_PROPAGATE(gemm_group(kTN, p, 2, st));
+    SET_PROPAGATE(gemm_group(dwm, p, 2, st));
     SET_PROPAGATE(colsum(s.denc_g, 4 * D, P * B, 4 * D, g.enc_x2h_b, 1, st));
     SET_PROPAGATE(colsum(s.denc_g, 4 * D, P * B, 4 * D, g.enc_h2h_b, 1, st));
     GemmProblem px = gemm_problem(P * B, D, s.demb_prev, D);
-    gemm_add_seg(px, s.denc_g, 4 * D, w.enc_x2h_w, D, 4 * D);
-    SET_PROPAGATE(gemm(kNN, px, st));
+    dx(px, s.denc_g, 4 * D, w.enc_x2h_w, s.t_enc_x2h, 4 * D, D, 0);
+    SET_PROPAGATE(gemm(dxm, px, st));
     SET_PROPAGATE(embed_bwd(prev, c.s.Wp, 1, s.emb_prev, s.demb_prev, g.embed, V, P, B, D, c.s.train, nullptr, st));
   }
+  SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
   return SET_OK;
 }
 
@@ -729,13 +817,14 @@ __global__ void rollout_dlogits_kernel(float* __restrict__ logits, int V, int B,
 }
 
 // packed cross-entropy (editnet.py:571-577)
-__global__ void __launch_bounds__(256) xe_loss_kernel(int B, int T, int V, int Wc, const float* __restrict__ pred,
+__global__ void __launch_bounds__(256) xe_loss_kernel(int B, int T, int V, int Wc, long stride_b, long stride_t,
+                                                      const float* __restrict__ pred,
                                                       const int64_t* __restrict__ caps,
                                                       const int* __restrict__ dec_len, float inv_count,
                                                       float* __restrict__ loss_out, float* __restrict__ dpred) {
   __shared__ float red[40];
   const int i = blockIdx.x / T, t = blockIdx.x % T;
-  const long off = ((long)i * T + t) * V;
+  const long off = (long)i * stride_b + (long)t * stride_t;
   const bool valid = dec_len[i] > t;
   if (!valid) {
     if (dpred) for (int v = threadIdx.x; v < V; v += blockDim.x) dpred[off + v] = 0.f;
@@ -834,7 +923,8 @@ int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const 
                            void* stream) {
   Ctx c;
   SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
-  SET_REQUIRE(feats && caps && decode_len_host && prev && prev_len && predictions, "null input");
+  SET_REQUIRE(feats && caps && decode_len_host && prev && prev_len, "null input");
+  SET_REQUIRE(predictions != nullptr || shape->train, "time-major logits live in the train-mode workspace");
   SET_REQUIRE(shape->Wc > shape->T, "caption width must exceed T");
   std::vector<int> bt;
   SET_PROPAGATE(batch_sizes(*shape, decode_len_host, bt));
@@ -848,6 +938,14 @@ int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const 
   for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
   SET_PROPAGATE(profile_mark(1, c.st));
   // vocabulary projection for all decoded rows at once (editnet.py:545-546), written batch-major
+  if (predictions == nullptr) {
+    // fused-trainer form: logits stay time-major [T][B][V] in the workspace (one dense GEMM operand later)
+    GemmProblem p = gemm_problem(T * B, V, c.ws.logits, V);
+    gemm_add_seg(p, c.ws.h2drop, D, w->fc_w, D, D);
+    p.bias = w->fc_b;
+    SET_PROPAGATE(gemm(kNT, p, c.st));
+    return SET_OK;
+  }
   SET_CHECK_CUDA(cudaMemsetAsync(predictions, 0, sizeof(float) * (size_t)B * T * V, c.st));
   GemmProblem p = gemm_problem(T * B, V, predictions, V);
   gemm_add_seg(p, c.ws.h2drop, D, w->fc_w, D, D);
@@ -864,13 +962,19 @@ int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const
                             size_t workspace_bytes, void* stream) {
   Ctx c;
   SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
-  SET_REQUIRE(grads && feats && caps && decode_len_host && prev && prev_len && d_predictions, "null input");
+  SET_REQUIRE(grads && feats && caps && decode_len_host && prev && prev_len, "null input");
   std::vector<int> bt;
   SET_PROPAGATE(batch_sizes(*shape, decode_len_host, bt));
   DLogits dl;
+  if (d_predictions == nullptr) {
+    // d logits were written time-major over the workspace logits by set_xe_loss_time_major()
+    SET_REQUIRE(shape->train, "time-major logits live in the train-mode workspace");
+    dl.p = c.ws.logits; dl.ld = dims->V; dl.inner = 0; dl.ld_inner = 0; dl.row_len = nullptr;
+    return backward_core(c, *grads, feats, caps, shape->Wc, 1, prev, prev_len, bt.data(), dl, c.ws.dec_len);
+  }
   dl.p = d_predictions; dl.ld = dims->V; dl.inner = shape->B; dl.ld_inner = (long)shape->T * dims->V;
   dl.row_len = c.ws.dec_len;  // uploaded by the forward call
-  return backward_core(c, *grads, feats, caps, shape->Wc, 1, prev, prev_len, bt.data(), dl);
+  return backward_core(c, *grads, feats, caps, shape->Wc, 1, prev, prev_len, bt.data(), dl, c.ws.dec_len);
 }
 
 int set_xe_loss(int B, int T, int V, int Wc, const float* predictions, const int64_t* caps,
@@ -879,11 +983,30 @@ int set_xe_loss(int B, int T, int V, int Wc, const float* predictions, const int
   SET_REQUIRE(B > 0 && T > 0 && V > 1 && Wc > T && predictions && caps && decode_len_dev && loss_out, "bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SET_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, 2 * sizeof(float), st));
-  xe_loss_kernel<<<B * T, 256, 0, st>>>(B, T, V, Wc, predictions, caps, decode_len_dev, inv_count, loss_out,
-                                        d_predictions);
+  xe_loss_kernel<<<B * T, 256, 0, st>>>(B, T, V, Wc, (long)T * V, (long)V, predictions, caps, decode_len_dev,
+                                        inv_count, loss_out, d_predictions);
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
   xe_count_kernel<<<1, 32, 0, st>>>(B, T, decode_len_dev, loss_out);
+  SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
+  return SET_OK;
+}
+
+int set_editnet_xe_loss_time_major(const SetDims* dims, const SetSeqShape* shape, const int64_t* caps,
+                                   float inv_count, float* loss_out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  Ctx c;
+  SetEditNetParams dummy;
+  SET_PROPAGATE(make_ctx(c, dims, shape, &dummy, workspace, workspace_bytes, 0, stream));
+  SET_REQUIRE(shape->train && caps && loss_out, "bad args");
+  const int B = shape->B, T = shape->T, V = dims->V;
+  SET_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, 2 * sizeof(float), c.st));
+  xe_loss_kernel<<<B * T, 256, 0, c.st>>>(B, T, V, shape->Wc, (long)V, (long)B * V, c.ws.logits, caps, c.ws.dec_len,
+                                          inv_count, loss_out, c.ws.logits);
+  SET_CHECK_CUDA(cudaGetLastError());
+  set_count_launch(1);
+  xe_count_kernel<<<1, 32, 0, c.st>>>(B, T, c.ws.dec_len, loss_out);
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
   return SET_OK;
@@ -942,7 +1065,7 @@ int set_editnet_rollout_backward(const SetDims* dims, const SetSeqShape* shape, 
   dl.p = s.logits; dl.ld = V; dl.inner = 0; dl.ld_inner = 0; dl.row_len = nullptr;
   // the embedding of step t was looked up from the token fed at step t (`it[t]`: <start>, then the
   // previous step's output token after the <end>/finished rewrite, editnet_rl.py:531-540)
-  return backward_core(c, *grads, feats, s.it, 1, B, prev, prev_len, bt.data(), dl);
+  return backward_core(c, *grads, feats, s.it, 1, B, prev, prev_len, bt.data(), dl, nullptr);
 }
 
 int set_reward_criterion(int B, int T, const float* seq_logprobs, const int64_t* seq, const float* reward,
@@ -978,6 +1101,18 @@ int set_profile_read(float* fwd_loop_ms, float* bwd_loop_ms) {
 int set_dropout_keep_mask(float* out, size_t n, uint64_t seed, int site, size_t base, void* stream) {
   SET_REQUIRE(out != nullptr, "null out");
   return dropout_keep_mask(out, (long)n, seed, (uint32_t)site, (long)base, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int set_gemm_backend(int backend) {
+  g_backend = backend;
+  return SET_OK;
+}
+
+int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset) {
+  if (tc_launches) *tc_launches = g_tc_launches;
+  if (simt_launches) *simt_launches = g_simt_launches;
+  if (reset) g_tc_launches = g_simt_launches = 0;
+  return SET_OK;
 }
 
 int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,

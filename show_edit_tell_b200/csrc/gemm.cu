@@ -206,8 +206,25 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, int M, int N
 
 }  // namespace
 
-int gemm_group(int mode, const GemmProblem* probs, int n, cudaStream_t stream) {
+int g_backend = 0;              // 0: tensor cores where eligible, 1: CUDA cores only
+long long g_tc_launches = 0, g_simt_launches = 0;
+
+int gemm_group(int mode, const GemmProblem* probs_in, int n, cudaStream_t stream) {
   SET_REQUIRE(n >= 1 && n <= 8, "1..8 problems per group");
+  GemmProblem probs[8];
+  int kept = 0;
+  for (int i = 0; i < n; ++i) {
+    if (probs_in[i].M <= 0 || probs_in[i].N <= 0) continue;
+    if (g_backend == 0) {
+      const int r = gemm_tc_try(mode, probs_in[i], stream);
+      if (r == SET_OK) { ++g_tc_launches; continue; }
+      if (r != -1) return r;
+    }
+    probs[kept++] = probs_in[i];
+  }
+  n = kept;
+  if (n == 0) return SET_OK;
+  ++g_simt_launches;
   GemmGroup g;
   memset(&g, 0, sizeof(g));
   // skinny problems get 32-wide column tiles so that more CTAs stream weights

@@ -52,7 +52,13 @@ inline void gemm_add_seg(GemmProblem& p, const float* A, long lda, const float* 
   s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K;
 }
 
-// Launch up to 8 independent problems of one mode in a single grid.
+// tensor-core path (gemm_tc.cu): SET_OK if launched, -1 if the problem is not eligible
+int gemm_tc_try(int mode, const GemmProblem& p, cudaStream_t stream);
+extern int g_backend;
+extern long long g_tc_launches, g_simt_launches;
+
+// Launch up to 8 independent problems of one mode (tensor cores where eligible, else one grouped
+// CUDA-core grid).
 int gemm_group(int mode, const GemmProblem* probs, int n, cudaStream_t stream);
 inline int gemm(int mode, const GemmProblem& p, cudaStream_t stream) { return gemm_group(mode, &p, 1, stream); }
 

@@ -54,15 +54,23 @@ class XETrainer:
         flat, st = self._ensure_state()
         call = dec._prepare_xe(image_features, image_mean, encoded_captions, caption_lengths,
                                encoded_previous_captions, previous_cap_length, seed=seed)
-        pred = dec._xe_forward_raw(call)
+        L = _lib.lib()
         s = call.shape
-        dec_dev = torch.tensor(call.decode_lengths, dtype=torch.int32, device=pred.device)
+        # logits stay time-major inside the workspace; the loss kernel turns them into d logits in place
+        check(L.set_editnet_xe_forward(
+            C.byref(call.dims), C.byref(s), C.byref(dec._struct), ptr(call.feats), ptr(call.image_mean),
+            ptr(call.caps), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, None, ptr(call.ws),
+            call.ws.numel(), _stream()))
         inv = 1.0 if self.distributed else 0.0   # DP: sums, normalised by the global count later
-        check(_lib.lib().set_xe_loss(s.B, s.T, dec.vocab_size, s.Wc, ptr(pred), ptr(call.caps), ptr(dec_dev), inv,
-                                     ptr(st["loss"]), ptr(pred), _stream()))
+        check(L.set_editnet_xe_loss_time_major(C.byref(call.dims), C.byref(s), ptr(call.caps), inv, ptr(st["loss"]),
+                                               ptr(call.ws), call.ws.numel(), _stream()))
         grad = st["grad"]
         grad.zero_()
-        dec._xe_backward_raw(call, pred, grad[:st["n"]])
+        g = dec._struct_for(grad[:st["n"]])
+        check(L.set_editnet_xe_backward(
+            C.byref(call.dims), C.byref(s), C.byref(dec._struct), C.byref(g), ptr(call.feats), ptr(call.caps),
+            call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, None, ptr(call.ws), call.ws.numel(),
+            _stream()))
         count_dev = None
         if self.distributed:
             grad[st["n"]:st["n"] + 1].copy_(st["loss"][1:2])
