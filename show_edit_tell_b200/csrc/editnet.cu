@@ -170,6 +170,7 @@ void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
     w.tscratch_floats = TB * (4 * D + D + D + (2 * D + F) + 4 * D + (2 * A + 2 * D) + 5 * D + V + D) +
                         (B + 4) * (4 * D + D + F + 2 * D) + BP * (A + D) + TBR * (A + D) + BRr * (D + F) +
                         PB * (4 * D + 2 * D) + 4096;
+    w.tscratch_floats = w.tscratch_floats * 2 + TB * (4 * D + (2 * D + F));   // column-block / row-range views repeat some matrices
     w.tscratch = ar.take<float>("tscratch", w.tscratch_floats);
   }
   w.total = ar.off;
