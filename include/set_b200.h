@@ -187,6 +187,8 @@ SET_API int set_editnet_workspace_lookup(const SetDims* dims, const SetSeqShape*
  * aligned operands, K >= 64), CUDA-core fp32 kernel otherwise; 1 = CUDA-core kernel only.  Both are
  * this library's own kernels; the switch exists for A/B parity tests and profiling. */
 SET_API int set_gemm_backend(int backend);
+/* debugging: device buffer (>= 16 x uint64) stamped with %globaltimer by CTA 0 of each tensor-core launch */
+SET_API int set_gemm_trace(void* buf);
 SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
 /* C = A @ B^T style contraction through the library's GEMM engine (mode 0 NT, 1 NN, 2 TN). */
 SET_API int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,

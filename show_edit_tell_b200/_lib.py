@@ -113,6 +113,7 @@ _SIGS = {
                                 C.c_float, C.c_float, _P, _P, _P]),
     "set_dropout_keep_mask": (C.c_int, [_P, C.c_size_t, C.c_uint64, C.c_int, C.c_size_t, _P]),
     "set_gemm_backend": (C.c_int, [C.c_int]),
+    "set_gemm_trace": (C.c_int, [_P]),
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_long, _P, C.c_long, _P, _P, C.c_long,
                            C.c_int, C.c_int, _P]),

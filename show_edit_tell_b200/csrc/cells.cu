@@ -7,6 +7,7 @@ namespace set {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kAttnThreads = 1024;   // one CTA per (sample, attention): latency-bound, so many warps
 
 inline int blocks_for(long n, int per_block) {
   long b = (n + per_block - 1) / per_block;
@@ -253,7 +254,7 @@ __global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restr
 
 // ------------------------------------------------------------------------ attention
 // dynamic smem: a2[A] | wv[A] | sc[max(P,R)] | red[40]
-__global__ void __launch_bounds__(kThreads) attention_fwd_kernel(const AttnFwdArgs a) {
+__global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnFwdArgs a) {
   extern __shared__ float sm[];
   const int A = a.A;
   float* a2 = sm;
@@ -275,8 +276,10 @@ __global__ void __launch_bounds__(kThreads) attention_fwd_kernel(const AttnFwdAr
     float s = 0.f;
     const float* row = att1 + (long)j * A;
     if (cap) {
+#pragma unroll 4
       for (int x = lane; x < A; x += 32) s += wv[x] * tanhf(row[x] + a2[x]);
     } else {
+#pragma unroll 4
       for (int x = lane; x < A; x += 32) s += wv[x] * fmaxf(row[x] + a2[x], 0.f);
     }
     s = warp_sum(s) + bias;
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(kThreads) attention_fwd_kernel(const AttnFwdAr
     const float* ph = a.prev_h + (long)i * a.P * a.D;
     for (int d = tid; d < a.D; d += blockDim.x) {
       float c = 0.f;
+#pragma unroll 6
       for (int j = 0; j < n; ++j) c += sc[j] * ph[(long)j * a.D + d];
       a.ctx[(long)i * a.D + d] = c;
     }
@@ -319,6 +323,7 @@ __global__ void __launch_bounds__(kThreads) attention_fwd_kernel(const AttnFwdAr
     const int F4 = a.F >> 2;
     for (int f4 = tid; f4 < F4; f4 += blockDim.x) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
       for (int r = 0; r < nvalid; ++r) {
         const float al = sc[r];
         const float4 v = __ldg(reinterpret_cast<const float4*>(ft + (long)r * a.F) + f4);
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) attention_fwd_kernel(const AttnFwdAr
 }
 
 // dynamic smem: a2[A] | wv[A] | al[n] | dal[n] | ds[n] | red[40]
-__global__ void __launch_bounds__(kThreads) attention_bwd_kernel(const AttnBwdArgs a) {
+__global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnBwdArgs a) {
   extern __shared__ float sm[];
   const int A = a.A;
   const bool cap = (blockIdx.y == 0);
@@ -358,6 +363,7 @@ __global__ void __launch_bounds__(kThreads) attention_bwd_kernel(const AttnBwdAr
     const float* dc = a.dctx + (long)i * a.D;
     for (int j = wid; j < n; j += nw) {
       float s = 0.f;
+#pragma unroll 8
       for (int d = lane; d < a.D; d += 32) s += dc[d] * ph[(long)j * a.D + d];
       if (j == js) {
         const float* pm = a.prev_m + ((long)i * a.P + j) * a.D;
@@ -372,8 +378,10 @@ __global__ void __launch_bounds__(kThreads) attention_bwd_kernel(const AttnBwdAr
     const float* di = a.datt_img + (long)i * a.ld_dimg;
     for (int r = wid; r < n; r += nw) {
       float s = 0.f;
-      if (r < nvalid)
+      if (r < nvalid) {
+#pragma unroll 8
         for (int f = lane; f < a.F; f += 32) s += di[f] * ft[(long)r * a.F + f];
+      }
       s = warp_sum(s);
       if (lane == 0) dal[r] = s;
     }
@@ -399,6 +407,7 @@ __global__ void __launch_bounds__(kThreads) attention_bwd_kernel(const AttnBwdAr
     float* dph = a.dprev_h + (long)i * a.P * a.D;
     for (int d = tid; d < a.D; d += blockDim.x) {
       const float g = dc[d];
+#pragma unroll 6
       for (int j = 0; j < n; ++j) dph[(long)j * a.D + d] += al[j] * g;
     }
     if (js >= 0) {
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(kThreads) attention_bwd_kernel(const AttnBwdAr
   for (int x = tid; x < A; x += blockDim.x) {
     float d2 = 0.f, dw = 0.f;
     const float av = a2[x], wx = wv[x];
+#pragma unroll 6
     for (int j = 0; j < n; ++j) {
       const float pre = att1[(long)j * A + x] + av;
       float y, dpre;
@@ -666,7 +676,7 @@ int attention_fwd(const AttnFwdArgs& a, cudaStream_t s) {
   const int n = a.P > a.R ? a.P : a.R;
   const size_t smem = sizeof(float) * (2 * a.A + n + 40);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  attention_fwd_kernel<<<dim3(a.b, 2), kThreads, smem, s>>>(a);
+  attention_fwd_kernel<<<dim3(a.b, 2), kAttnThreads, smem, s>>>(a);
   LAUNCH_OK();
 }
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
@@ -674,7 +684,7 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   const int n = a.P > a.R ? a.P : a.R;
   const size_t smem = sizeof(float) * (2 * a.A + 3 * n + 40);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  attention_bwd_kernel<<<dim3(a.b, 2), kThreads, smem, s>>>(a);
+  attention_bwd_kernel<<<dim3(a.b, 2), kAttnThreads, smem, s>>>(a);
   LAUNCH_OK();
 }
 int ctx_gate_fwd(const float* s4, long ld_s4, const float* th, long ld_th, float* zst, float* att_cap,

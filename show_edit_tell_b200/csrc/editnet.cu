@@ -1104,6 +1104,11 @@ int set_dropout_keep_mask(float* out, size_t n, uint64_t seed, int site, size_t 
   return dropout_keep_mask(out, (long)n, seed, (uint32_t)site, (long)base, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int set_gemm_trace(void* buf) {
+  gemm_tc_set_trace(reinterpret_cast<unsigned long long*>(buf));
+  return SET_OK;
+}
+
 int set_gemm_backend(int backend) {
   g_backend = backend;
   return SET_OK;

@@ -54,6 +54,7 @@ inline void gemm_add_seg(GemmProblem& p, const float* A, long lda, const float* 
 
 // tensor-core path (gemm_tc.cu): SET_OK if launched, -1 if the problem is not eligible
 int gemm_tc_try(int mode, const GemmProblem& p, cudaStream_t stream);
+void gemm_tc_set_trace(unsigned long long* buf);
 extern int g_backend;
 extern long long g_tc_launches, g_simt_launches;
 

@@ -50,7 +50,18 @@ struct TcParams {
   const float* add; long ldadd; int add_mod;
   int beta, act;
   unsigned idesc_xor;              // debugging aid (SET_TC_IDESC_XOR)
+  unsigned long long* trace;       // debugging aid: per-phase %globaltimer stamps of CTA 0 (SET_TC_TRACE)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot)                                                         \
+  do {                                                                         \
+    if (prm.trace && blockIdx.x == 0) prm.trace[slot] = gtimer();              \
+  } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -136,6 +147,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   uint8_t* gen_base = smem_dyn + (base - smem_u32(smem_dyn));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 64) TC_STAMP(0);
 
   // tile / split decode
   int bid = blockIdx.x;
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  if (threadIdx.x == 64) TC_STAMP(1);
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
       const int s = i % S;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
       mbar_wait(full_bar(s), ph);
+      if (ct == 0 && i == 0) TC_STAMP(2);
       uint8_t* st = gen_base + s * Cfg::kStageBytes;
       float4* p_hi = reinterpret_cast<float4*>(st);
       float4* p_lo = reinterpret_cast<float4*>(st + Cfg::kPBytes);
@@ -265,17 +279,24 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(conv_bar(s));
+      if (ct == 0 && i == 0) TC_STAMP(3);
+      if (ct == 0 && i == nkb - 1) TC_STAMP(4);
     }
     // ---- epilogue
     if (nkb > 0) {
       mbar_wait(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    // Accumulator -> registers -> shared (the pipeline stages are idle now) so that global traffic is
-    // coalesced in both orientations and the per-element epilogue stays a compact loop.
+    if (ct == 0) TC_STAMP(5);
+    // Accumulator -> registers -> shared (the pipeline stages are idle now).  The tile is staged in the
+    // orientation of the OUTPUT rows (transposed for swap mode) so that the second phase reads float4
+    // along the contiguous global direction: 128-bit global loads/stores/reductions, several rows in
+    // flight per thread, no serial latency chain.
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    constexpr int EPLD = QN + 1;               // padded row: conflict-free column reads
-    float* ep = reinterpret_cast<float*>(gen_base) + (size_t)quarter * 32 * EPLD;
+    constexpr int EPW_N = QN + 4;              // staged row pitch, non-swap: [128 p][QN q]
+    constexpr int EPW_S = kTileP + 4;          // staged row pitch, swap:     [QN q][128 p]
+    float* ep = reinterpret_cast<float*>(gen_base);
+    const int prow = quarter * 32 + lane;      // tile row held by this thread
 #pragma unroll 1
     for (int cb = 0; cb < QN / 32; ++cb) {
       uint32_t r[32];
@@ -285,54 +306,75 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
+      if (prm.swap) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) ep[lane * EPLD + cb * 32 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) ep[(cb * 32 + j) * EPW_S + prow] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(&ep[prow * EPW_N + cb * 32 + j]) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
+      }
     }
-    __syncwarp();
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    if (ct == 0) TC_STAMP(6);
     const bool lead = (ks == 0);               // split 0 carries bias / addend
     const bool atomic = prm.split_k > 1;
-    auto finish = [&](float v, int m, int n, float* cp) {
+    const int width = prm.swap ? kTileP : QN;  // contiguous extent of a staged row
+    const int pitch = prm.swap ? EPW_S : EPW_N;
+    const int m_base = prm.swap ? q0 : p0, n_base = prm.swap ? p0 : q0;
+    const int m_lim = prm.swap ? prm.Qr : prm.Pr, n_lim = prm.swap ? prm.Pr : prm.Qr;
+    const int vec_per_row = width / 4;
+    const int total_vec = (prm.swap ? QN : kTileP) * vec_per_row;
+#pragma unroll 4
+    for (int e = ct; e < total_vec; e += 128) {
+      const int o = e / vec_per_row, i4 = (e % vec_per_row) * 4;
+      const int m = m_base + o, n = n_base + i4;
+      if (m >= m_lim || n >= n_lim) continue;
+      if (prm.c_row_len && !(prm.c_row_len[m % prm.c_valid_inner] > m / prm.c_valid_inner)) continue;
+      const float4 acc = *reinterpret_cast<const float4*>(&ep[o * pitch + i4]);
+      float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      float* cp = prm.C + (prm.c_inner > 0 ? (long)(m / prm.c_inner) * prm.ldc + (long)(m % prm.c_inner) * prm.c_ld_inner
+                                           : (long)m * prm.ldc) + n;
+      const int nv = min(4, n_lim - n);
+      const bool vec_ok = (nv == 4) && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
       if (!atomic || lead) {
-        if (prm.bias) v += __ldg(prm.bias + n);
-        if (prm.bias2) v += __ldg(prm.bias2 + n);
-        if (prm.add) v += prm.add[(long)(prm.add_mod ? m % prm.add_mod : m) * prm.ldadd + n];
+        if (prm.bias)
+          for (int k = 0; k < nv; ++k) v[k] += __ldg(prm.bias + n + k);
+        if (prm.bias2)
+          for (int k = 0; k < nv; ++k) v[k] += __ldg(prm.bias2 + n + k);
+        if (prm.add) {
+          const float* ap = prm.add + (long)(prm.add_mod ? m % prm.add_mod : m) * prm.ldadd + n;
+          for (int k = 0; k < nv; ++k) v[k] += ap[k];
+        }
       }
-      if (atomic) { atomicAdd(cp, v); return; }
-      if (prm.act == 1) v = fmaxf(v, 0.f);
-      else if (prm.act == 2) v = tanhf(v);
-      if (prm.beta) v += *cp;
-      *cp = v;
-    };
-    const int pq = p0 + quarter * 32;           // first P row of this warp
-    if (prm.swap) {
-      // (m, n) = (q, p): lanes run along n
-      const int n = pq + lane;
-      const int qmax = min(QN, prm.Qr - q0);
-      if (n < prm.Pr)
-#pragma unroll 1
-        for (int c = 0; c < qmax; ++c) {
-          const int m = q0 + c;
-          finish(ep[lane * EPLD + c], m, n, prm.C + (long)m * prm.ldc + n);
+      if (atomic) {
+        if (vec_ok) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3]) : "memory");
+        } else {
+          for (int k = 0; k < nv; ++k) atomicAdd(cp + k, v[k]);
         }
-    } else {
-      // (m, n) = (p, q): one row at a time, lanes run along n
-      const int rmax = min(32, prm.Pr - pq);
-#pragma unroll 1
-      for (int rr = 0; rr < rmax; ++rr) {
-        const int m = pq + rr;
-        if (prm.c_row_len && !(prm.c_row_len[m % prm.c_valid_inner] > m / prm.c_valid_inner)) continue;
-        float* crow = prm.C + (prm.c_inner > 0 ? (long)(m / prm.c_inner) * prm.ldc + (long)(m % prm.c_inner) * prm.c_ld_inner
-                                               : (long)m * prm.ldc);
-#pragma unroll 1
-        for (int c = lane; c < QN; c += 32) {
-          const int n = q0 + c;
-          if (n < prm.Qr) finish(ep[rr * EPLD + c], m, n, crow + n);
+        continue;
+      }
+      if (prm.act == 1) { for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.f); }
+      else if (prm.act == 2) { for (int k = 0; k < 4; ++k) v[k] = tanhf(v[k]); }
+      if (vec_ok) {
+        if (prm.beta) {
+          const float4 old = *reinterpret_cast<const float4*>(cp);
+          v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
         }
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        for (int k = 0; k < nv; ++k) cp[k] = prm.beta ? cp[k] + v[k] : v[k];
       }
     }
   }
+  if (threadIdx.x == 64) TC_STAMP(7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 64) TC_STAMP(8);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)QN) : "memory");
   }
@@ -373,6 +415,8 @@ bool make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, i
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+unsigned long long* g_tc_trace = nullptr;
 
 bool aligned_ok(const float* p, long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 4) == 0; }
 
@@ -444,6 +488,7 @@ int gemm_tc_try(int mode, const GemmProblem& g, cudaStream_t stream) {
   prm.bias = g.bias; prm.bias2 = g.bias2; prm.add = g.add; prm.ldadd = g.ldadd; prm.add_mod = g.add_mod;
   prm.beta = g.beta; prm.act = g.act;
   { const char* e = getenv("SET_TC_IDESC_XOR"); prm.idesc_xor = e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }
+  prm.trace = g_tc_trace;
   if (split > 1 && !g.beta) {
     // partial sums meet in global atomics: clear the destination first
     if (g.c_inner > 0 || g.c_row_len) return -1;
@@ -456,5 +501,8 @@ int gemm_tc_try(int mode, const GemmProblem& g, cudaStream_t stream) {
   set_count_launch(1);
   return SET_OK;
 }
+
+// debugging: device buffer of >= 16 u64 that CTA 0 of every following tensor-core launch stamps
+void gemm_tc_set_trace(unsigned long long* buf) { g_tc_trace = buf; }
 
 }  // namespace set

@@ -59,7 +59,7 @@ def test_tc_gemm_matches_fp64(mode, M, N, K):
         assert tc == 0 and simt == 1
     ref = ref + bias.double() + C0.double()
     err = float((Cm.double() - ref).abs().max())
-    tol = 2e-5 * float(ref.abs().max())
+    tol = 2e-5 * float(ref.abs().max()) * max(1.0, K / 2048)   # RZ bias grows with the accumulation chain
     print("mode %d %dx%dx%d: max abs err %.3e (tol %.3e)" % (mode, M, N, K, err, tol))
     assert err < tol
     # beta = 0, relu epilogue, vs the CUDA-core kernel bit-for-bit-ish
