@@ -153,6 +153,46 @@ SET_API int set_editnet_rollout_backward(const SetDims* dims, const SetSeqShape*
                                  const int64_t* prev_len, uint64_t seed, const float* d_seq_logprobs,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DCNet (text-only denoising auto-encoder): DAE of dcnet.py:273-350 / dcnet_rl.py:273-346.
+ * SetDims: D = decoder_dim = emb_dim = 2 * caption_features_dim (the reference's concatenations force
+ * this, dcnet.py:286-291), A = attention_dim, F unused.  SetSeqShape: R and adaptive unused. */
+typedef struct SetDcNetParams {
+  float* embed;                                          /* embed.embedding.weight            [V,D]    */
+  float *enc_wih_f, *enc_whh_f, *enc_bih_f, *enc_bhh_f;  /* caption_encoder.lstm_encoder.*_l0 [4C,D],[4C,C] */
+  float *enc_wih_r, *enc_whh_r, *enc_bih_r, *enc_bhh_r;  /* caption_encoder.lstm_encoder.*_l0_reverse   */
+  float *enc_cat_w, *enc_cat_b;                          /* caption_encoder.concat            [2C,2C]  */
+  float *ca_feat_w, *ca_feat_b;                          /* caption_attention.cap_features_att [A,2C]  */
+  float *ca_dec_w, *ca_dec_b;                            /* caption_attention.cap_decoder_att  [A,D]   */
+  float *ca_full_w, *ca_full_b;                          /* caption_attention.cap_full_att     [1,A]   */
+  float *al_wih, *al_whh, *al_bih, *al_bhh;              /* attention_lstm [4D,3D],[4D,D]              */
+  float *ll_wih, *ll_whh, *ll_bih, *ll_bhh;              /* language_lstm  [4D,2D],[4D,D]              */
+  float *fc_w, *fc_b;                                    /* fc [V,D]                                   */
+} SetDcNetParams;
+
+SET_API size_t set_dcnet_workspace_bytes(const SetDims* dims, const SetSeqShape* shape);
+SET_API int set_dcnet_workspace_lookup(const SetDims* dims, const SetSeqShape* shape, const char* name,
+                               size_t* offset, size_t* bytes);
+/* Teacher-forced forward / backward: replace DAE.forward (dcnet.py:303-350) and its autograd replay.
+ * Arguments as for the EditNet entry points, without image inputs. */
+SET_API int set_dcnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w,
+                         const int64_t* caps, const int* decode_len_host, const int64_t* prev,
+                         const int64_t* prev_len, uint64_t seed, float* predictions, void* workspace,
+                         size_t workspace_bytes, void* stream);
+SET_API int set_dcnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w,
+                          const SetDcNetParams* grads, const int64_t* caps, const int* decode_len_host,
+                          const int64_t* prev, const int64_t* prev_len, uint64_t seed,
+                          const float* d_predictions, void* workspace, size_t workspace_bytes, void* stream);
+/* Rollout / its backward: replace DAE.forward of dcnet_rl.py:286-346 (modes as set_editnet_rollout). */
+SET_API int set_dcnet_rollout(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w,
+                      const int64_t* prev, const int64_t* prev_len, int64_t start_token, int64_t end_token,
+                      int mode, const int64_t* forced, uint64_t seed, int64_t* seq, float* seq_logprobs,
+                      void* workspace, size_t workspace_bytes, void* stream);
+SET_API int set_dcnet_rollout_backward(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w,
+                               const SetDcNetParams* grads, const int64_t* prev, const int64_t* prev_len,
+                               uint64_t seed, const float* d_seq_logprobs, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* SCST loss: replaces RewardCriterion.forward, editnet_rl.py:557-573.  loss_out[0] = loss;
  * d_logprobs [B,T] (optional) = d loss / d seq_logprobs. */
 SET_API int set_reward_criterion(int B, int T, const float* seq_logprobs, const int64_t* seq, const float* reward,

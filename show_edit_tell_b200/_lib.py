@@ -71,6 +71,41 @@ class SetEditNetParams(C.Structure):
     _fields_ = [(name, C.c_void_p) for name, _ in EDITNET_FIELDS]
 
 
+DCNET_FIELDS = [
+    ("embed", "embed.embedding.weight"),
+    ("enc_wih_f", "caption_encoder.lstm_encoder.weight_ih_l0"),
+    ("enc_whh_f", "caption_encoder.lstm_encoder.weight_hh_l0"),
+    ("enc_bih_f", "caption_encoder.lstm_encoder.bias_ih_l0"),
+    ("enc_bhh_f", "caption_encoder.lstm_encoder.bias_hh_l0"),
+    ("enc_wih_r", "caption_encoder.lstm_encoder.weight_ih_l0_reverse"),
+    ("enc_whh_r", "caption_encoder.lstm_encoder.weight_hh_l0_reverse"),
+    ("enc_bih_r", "caption_encoder.lstm_encoder.bias_ih_l0_reverse"),
+    ("enc_bhh_r", "caption_encoder.lstm_encoder.bias_hh_l0_reverse"),
+    ("enc_cat_w", "caption_encoder.concat.weight"),
+    ("enc_cat_b", "caption_encoder.concat.bias"),
+    ("ca_feat_w", "caption_attention.cap_features_att.weight"),
+    ("ca_feat_b", "caption_attention.cap_features_att.bias"),
+    ("ca_dec_w", "caption_attention.cap_decoder_att.weight"),
+    ("ca_dec_b", "caption_attention.cap_decoder_att.bias"),
+    ("ca_full_w", "caption_attention.cap_full_att.weight"),
+    ("ca_full_b", "caption_attention.cap_full_att.bias"),
+    ("al_wih", "attention_lstm.weight_ih"),
+    ("al_whh", "attention_lstm.weight_hh"),
+    ("al_bih", "attention_lstm.bias_ih"),
+    ("al_bhh", "attention_lstm.bias_hh"),
+    ("ll_wih", "language_lstm.weight_ih"),
+    ("ll_whh", "language_lstm.weight_hh"),
+    ("ll_bih", "language_lstm.bias_ih"),
+    ("ll_bhh", "language_lstm.bias_hh"),
+    ("fc_w", "fc.weight"),
+    ("fc_b", "fc.bias"),
+]
+
+
+class SetDcNetParams(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _ in DCNET_FIELDS]
+
+
 def build(verbose=False):
     """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     out = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
@@ -108,6 +143,18 @@ _SIGS = {
     "set_editnet_rollout_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape),
                                                C.POINTER(SetEditNetParams), C.POINTER(SetEditNetParams), _P, _P, _P,
                                                C.c_uint64, _P, _P, C.c_size_t, _P]),
+    "set_dcnet_workspace_bytes": (C.c_size_t, [C.POINTER(SetDims), C.POINTER(SetSeqShape)]),
+    "set_dcnet_workspace_lookup": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.c_char_p,
+                                             C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "set_dcnet_xe_forward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams), _P,
+                                       C.POINTER(C.c_int), _P, _P, C.c_uint64, _P, _P, C.c_size_t, _P]),
+    "set_dcnet_xe_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams),
+                                        C.POINTER(SetDcNetParams), _P, C.POINTER(C.c_int), _P, _P, C.c_uint64, _P, _P,
+                                        C.c_size_t, _P]),
+    "set_dcnet_rollout": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams), _P, _P,
+                                    C.c_int64, C.c_int64, C.c_int, _P, C.c_uint64, _P, _P, _P, C.c_size_t, _P]),
+    "set_dcnet_rollout_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams),
+                                             C.POINTER(SetDcNetParams), _P, _P, C.c_uint64, _P, _P, C.c_size_t, _P]),
     "set_reward_criterion": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "set_clip_adam": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _P, _P, _P]),

@@ -241,6 +241,68 @@ __global__ void enc_lstm_bwd_kernel(const float* __restrict__ gates, const float
   }
 }
 
+__global__ void bilstm_fwd_kernel(const float* __restrict__ hh_pre, const float* __restrict__ xg,
+                                  const int64_t* __restrict__ len, int s, int reverse,
+                                  const float* __restrict__ h_prev, const float* __restrict__ c_prev,
+                                  float* __restrict__ h_out, float* __restrict__ c_out, float* __restrict__ gates,
+                                  float* __restrict__ out, long out_ld_row, long out_ld_pos, int B, int P, int C) {
+  const long total = (long)B * C;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % C);
+    const long i = x / C;
+    const long L = len[i];
+    float* g = gates + i * 4 * C;
+    if (L <= s) {
+      g[d] = 0.f; g[C + d] = 0.f; g[2 * C + d] = 0.f; g[3 * C + d] = 0.f;
+      h_out[x] = h_prev[x];
+      c_out[x] = c_prev[x];
+      continue;
+    }
+    const long pos = reverse ? L - 1 - s : s;
+    const float* px = xg + (i * P + pos) * 4 * C;
+    float pi = px[d], pf = px[C + d], pg = px[2 * C + d], po = px[3 * C + d];
+    if (hh_pre) {
+      const float* ph = hh_pre + i * 4 * C;
+      pi += ph[d]; pf += ph[C + d]; pg += ph[2 * C + d]; po += ph[3 * C + d];
+    }
+    const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf(pg), go = sigmoidf_(po);
+    const float c = gf * c_prev[x] + gi * gg;
+    const float h = go * tanhf(c);
+    g[d] = gi; g[C + d] = gf; g[2 * C + d] = gg; g[3 * C + d] = go;
+    c_out[x] = c;
+    h_out[x] = h;
+    out[i * out_ld_row + pos * out_ld_pos + d] = h;
+  }
+}
+
+__global__ void bilstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                  const float* __restrict__ c_cur, float* __restrict__ dh_run,
+                                  float* __restrict__ dc_run, const float* __restrict__ dout, long out_ld_row,
+                                  long out_ld_pos, const float* __restrict__ dh_last, long ld_dh_last,
+                                  const int64_t* __restrict__ len, int s, int reverse, float* __restrict__ dgates,
+                                  float* __restrict__ dxg, int B, int P, int C) {
+  const long total = (long)B * C;
+  for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(x % C);
+    const long i = x / C;
+    const long L = len[i];
+    float* dg = dgates + i * 4 * C;
+    if (L <= s) {
+      dg[d] = 0.f; dg[C + d] = 0.f; dg[2 * C + d] = 0.f; dg[3 * C + d] = 0.f;
+      continue;
+    }
+    const long pos = reverse ? L - 1 - s : s;
+    const float* g = gates + i * 4 * C;
+    float dhv = dh_run[x] + dout[i * out_ld_row + pos * out_ld_pos + d];
+    if (L - 1 == s) dhv += dh_last[i * ld_dh_last + d];     // this direction's final state feeds `concat`
+    float dcp;
+    lstm_bwd_core(g[d], g[C + d], g[2 * C + d], g[3 * C + d], c_prev[x], c_cur[x], dhv, dc_run[x], dg, C, d, dcp);
+    dc_run[x] = dcp;
+    float* dx = dxg + (i * P + pos) * 4 * C;
+    dx[d] = dg[d]; dx[C + d] = dg[C + d]; dx[2 * C + d] = dg[2 * C + d]; dx[3 * C + d] = dg[3 * C + d];
+  }
+}
+
 __global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restrict__ mask, long rows, int D) {
   // warp per (i,p) row
   const int lane = threadIdx.x & 31;
@@ -307,7 +369,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnF
       float c = 0.f;
 #pragma unroll 6
       for (int j = 0; j < n; ++j) c += sc[j] * ph[(long)j * a.D + d];
-      a.ctx[(long)i * a.D + d] = c;
+      a.ctx[(long)i * (a.ld_ctx ? a.ld_ctx : a.D) + d] = c;
     }
     if (a.prev_m) {
       int js = 0; float best = sc[0];
@@ -360,7 +422,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
   // d alpha_j = <dcontext, value_j> (+ select term)
   if (cap) {
     const float* ph = a.prev_h + (long)i * a.P * a.D;
-    const float* dc = a.dctx + (long)i * a.D;
+    const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
     for (int j = wid; j < n; j += nw) {
       float s = 0.f;
 #pragma unroll 8
@@ -403,7 +465,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
   if (tid == 0) atomicAdd(cap ? a.dcap_b : a.dvis_b, dbias);
   // value gradients
   if (cap) {
-    const float* dc = a.dctx + (long)i * a.D;
+    const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
     float* dph = a.dprev_h + (long)i * a.P * a.D;
     for (int d = tid; d < a.D; d += blockDim.x) {
       const float g = dc[d];
@@ -663,6 +725,22 @@ int enc_lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, fl
   if (rows <= 0) return SET_OK;
   enc_lstm_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
       gates, c_prev, c_cur, dh_run, dc_run, dseq_h, dseq_m, seq_ld, dh_last, len, t, dgates, rows, D);
+  LAUNCH_OK();
+}
+int bilstm_fwd(const float* hh_pre, const float* xg, const int64_t* len, int s, int reverse, const float* h_prev,
+               const float* c_prev, float* h_out, float* c_out, float* gates, float* out, long out_ld_row,
+               long out_ld_pos, int B, int P, int C, cudaStream_t st) {
+  bilstm_fwd_kernel<<<blocks_for((long)B * C, kThreads), kThreads, 0, st>>>(
+      hh_pre, xg, len, s, reverse, h_prev, c_prev, h_out, c_out, gates, out, out_ld_row, out_ld_pos, B, P, C);
+  LAUNCH_OK();
+}
+int bilstm_bwd(const float* gates, const float* c_prev, const float* c_cur, float* dh_run, float* dc_run,
+               const float* dout, long out_ld_row, long out_ld_pos, const float* dh_last, long ld_dh_last,
+               const int64_t* len, int s, int reverse, float* dgates, float* dxg, int B, int P, int C,
+               cudaStream_t st) {
+  bilstm_bwd_kernel<<<blocks_for((long)B * C, kThreads), kThreads, 0, st>>>(
+      gates, c_prev, c_cur, dh_run, dc_run, dout, out_ld_row, out_ld_pos, dh_last, ld_dh_last, len, s, reverse,
+      dgates, dxg, B, P, C);
   LAUNCH_OK();
 }
 int enc_mask(const float* prev_m, float* mask, int B, int P, int D, cudaStream_t s) {

@@ -44,6 +44,17 @@ int lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, const 
 int enc_lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, float* dh_run, float* dc_run,
                  const float* dseq_h, const float* dseq_m, long seq_ld, const float* dh_last,
                  const int64_t* len, int t, float* dgates, int rows, int D, cudaStream_t s);
+// One step of one direction of the packed bidirectional nn.LSTM of DCNet's caption encoder
+// (dcnet.py:217,233).  Row i works on position pos = reverse ? len[i]-1-s : s and is active iff
+// s < len[i]; inactive rows keep their state.  pre = xg[i][pos] (+ hh_pre[i]); out[i][pos][col0..col0+C) = h.
+int bilstm_fwd(const float* hh_pre, const float* xg, const int64_t* len, int s, int reverse, const float* h_prev,
+               const float* c_prev, float* h_out, float* c_out, float* gates, float* out, long out_ld_row,
+               long out_ld_pos, int B, int P, int C, cudaStream_t st);
+// reverse of the above: dgates (also scattered to dxg[i][pos]), carries dh_run / dc_run
+int bilstm_bwd(const float* gates, const float* c_prev, const float* c_cur, float* dh_run, float* dc_run,
+               const float* dout, long out_ld_row, long out_ld_pos, const float* dh_last, long ld_dh_last,
+               const int64_t* len, int s, int reverse, float* dgates, float* dxg, int B, int P, int C,
+               cudaStream_t st);
 // mask[i][p] = (sum_d prev_m[i][p][d] != 0)  (editnet.py:340)
 int enc_mask(const float* prev_m, float* mask, int B, int P, int D, cudaStream_t s);
 // y = dy * (1 - y^2) in place on dy (tanh backward)
@@ -61,7 +72,8 @@ struct AttnFwdArgs {
   const float* prev_h;  // [B][P][D]
   const float* prev_m;  // [B][P][D] (null: no select -- DCNet)
   float* alpha_c;       // [b][P]
-  float* ctx;           // [b][D]
+  float* ctx;           // row i at ctx + i*ld_ctx (ld_ctx == 0 means D)
+  long ld_ctx;
   float* sel;           // [b][D]
   int* sel_idx;         // [b]
   // visual attention (editnet.py:442-446; adaptive :449-456)
@@ -80,7 +92,8 @@ struct AttnBwdArgs {
   int b, P, R, D, A, F;
   const float* att1c; const float* s2; long ld_s2; const float* cap_w; const float* mask;
   const float* prev_h; const float* prev_m; const float* alpha_c; const int* sel_idx;
-  const float* dctx;      // [b][D]
+  const float* dctx;      // row i at dctx + i*ld_dctx (0 means D)
+  long ld_dctx;
   const float* dsel;      // [b][D] (null: no select)
   float* dprev_h;         // [B][P][D] +=
   float* dprev_m;         // [B][P][D] +=

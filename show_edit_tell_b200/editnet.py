@@ -194,15 +194,25 @@ class EditNetBase(nn.Module):
         self._struct = None
         self.last_seed = None
 
+    def __getstate__(self):
+        # ctypes structs / cached calls are rebuilt lazily; parameters are pickled as ordinary tensors
+        state = self.__dict__.copy()
+        for k in ("_flat", "_offsets", "_struct", "_last_call"):
+            state[k] = None
+        return state
+
     def init_hidden_state(self, batch_size):
         dev = self.fc.weight.device
         return (torch.zeros(batch_size, self.decoder_dim, device=dev),
                 torch.zeros(batch_size, self.decoder_dim, device=dev))
 
+    FIELDS = EDITNET_FIELDS
+    STRUCT = SetEditNetParams
+
     # ---- flat parameter storage: every parameter is a view into one buffer, so the optimizer
     # tail and the data-parallel all-reduce see a single tensor
     def _ordered_params(self):
-        return [self.get_parameter(key) for _, key in EDITNET_FIELDS]
+        return [self.get_parameter(key) for _, key in self.FIELDS]
 
     def flatten_parameters(self):
         params = self._ordered_params()
@@ -221,8 +231,8 @@ class EditNetBase(nn.Module):
             view.copy_(p.data)
             p.data = view
         self._flat, self._offsets = flat, offs
-        st = SetEditNetParams()
-        for (name, _), p in zip(EDITNET_FIELDS, params):
+        st = self.STRUCT()
+        for (name, _), p in zip(self.FIELDS, params):
             setattr(st, name, p.data_ptr())
         self._struct = st
         return flat
@@ -231,8 +241,8 @@ class EditNetBase(nn.Module):
         return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self._ordered_params(), self._offsets)]
 
     def _struct_for(self, flat):
-        st = SetEditNetParams()
-        for (name, _), v in zip(EDITNET_FIELDS, self._views(flat)):
+        st = self.STRUCT()
+        for (name, _), v in zip(self.FIELDS, self._views(flat)):
             setattr(st, name, v.data_ptr())
         return st
 
