@@ -21,6 +21,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check, ptr
 from .editnet import _stream
+from .parallel import allreduce_sums
 
 
 class XETrainer:
@@ -73,9 +74,7 @@ class XETrainer:
             _stream()))
         count_dev = None
         if self.distributed:
-            grad[st["n"]:st["n"] + 1].copy_(st["loss"][1:2])
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
-            count_dev = grad[st["n"]:st["n"] + 1]
+            count_dev = allreduce_sums(grad, st["n"], st["loss"][1], self.group)
         self.step_count += 1
         check(_lib.lib().set_clip_adam(ptr(flat), ptr(grad), ptr(st["m"]), ptr(st["v"]), st["n"], self.step_count,
                                        self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
