@@ -85,7 +85,7 @@ void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
   w.logits = ar.take<float>("logits", Tv * B * V);   // rollouts only use it; XE writes to `predictions`
   w.lse = ar.take<float>("lse", T * B);
   w.scratch4d = ar.take<float>("scratch4d", B * 4 * D);
-  w.s4 = ar.take<float>("s4", B * 3 * D);
+  w.s4 = ar.take<float>("s4", T * B * 3 * D);
   w.ones = ar.take<float>("ones", T * B);
   w.sel_idx = ar.take<int>("sel_idx", T * B);
   w.nreg = ar.take<int>("nreg", B);
@@ -113,15 +113,15 @@ void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
   w.demb_prev = ar.take<float>("demb_prev", P * B * D);
   w.denc_g = ar.take<float>("denc_g", P * B * 4 * D);
   w.dh_last = ar.take<float>("dh_last", B * D);
-  w.dh_run = ar.take<float>("dh_run", B * D);
+  w.dh_run = ar.take<float>("dh_run", P * B * D);
   w.dc_run = ar.take<float>("dc_run", B * D);
   w.sumG1 = ar.take<float>("sumG1", B * 4 * D);
-  w.dh2c = ar.take<float>("dh2c", B * D);
+  w.dh2c = ar.take<float>("dh2c", (T + 1) * B * D);
   w.dc2c = ar.take<float>("dc2c", B * D);
-  w.dh1c = ar.take<float>("dh1c", B * D);
+  w.dh1c = ar.take<float>("dh1c", (T + 1) * B * D);
   w.dc1c = ar.take<float>("dc1c", B * D);
-  w.dX2 = ar.take<float>("dX2", B * (2 * D + F));
-  w.dctx = ar.take<float>("dctx", B * D);
+  w.dX2 = ar.take<float>("dX2", T * B * (2 * D + F));
+  w.dctx = ar.take<float>("dctx", T * B * D);
   w.dsel = ar.take<float>("dsel", B * D);
   w.dcnew = ar.take<float>("dcnew", B * D);
   w.regionB_end = ar.off;
@@ -218,11 +218,14 @@ int prepare_common(Ctx& c, const float* feats, const float* image_mean_in, const
     SET_PROPAGATE(gemm(kNT, p, st));
   }
   for (int t = 0; t < P; ++t) {
-    GemmProblem p = gemm_problem(B, 4 * D, s.scratch4d, 4 * D);
+    // Every GEMM output below lands in a slab of the workspace that the region memset already zeroed
+    // (c_zeroed): split-K launches then need no memset of their own.
+    float* pre = s.enc_gates + (size_t)t * B * 4 * D;   // pre-activations, converted in place by lstm_fwd
+    GemmProblem p = gemm_problem(B, 4 * D, pre, 4 * D);
     if (t > 0) gemm_add_seg(p, s.enc_h + (size_t)t * B * D, D, w.enc_h2h_w, D, D);
-    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D;
+    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(lstm_fwd(s.scratch4d, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
+    SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
                            s.enc_gates + (size_t)t * B * 4 * D, s.enc_c + (size_t)(t + 1) * B * D,
                            s.enc_h + (size_t)(t + 1) * B * D, D, B, D, prev_len, t, s.prev_h, s.prev_m,
                            (long)P * D, st));
@@ -287,6 +290,7 @@ int project_words(Ctx& c, int t0, int nt) {
   Ws& s = c.ws;
   const size_t r0 = (size_t)t0 * B;
   GemmProblem p[3];
+  memset(p, 0, sizeof(p));
   p[0] = gemm_problem(nt * B, 4 * D, s.pre1 + r0 * 4 * D, 4 * D);
   gemm_add_seg(p[0], s.emb_all + r0 * D, D, w.al_wih, 3 * D + F, D);
   p[0].add = s.pre1s; p[0].ldadd = 4 * D; p[0].add_mod = B;
@@ -296,6 +300,7 @@ int project_words(Ctx& c, int t0, int nt) {
   p[2] = gemm_problem(nt * B, D, s.tw + r0 * D, D);
   gemm_add_seg(p[2], s.emb_all + r0 * D, D, w.ca_tc_w, 2 * D, D);
   p[2].bias = w.ca_tc_b;
+  p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = 1;
   return gemm_group(kNT, p, 3, c.st);
 }
 
@@ -310,15 +315,17 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
   float* s2t = s.s2 + (size_t)t * B * LS2;
   float* g2t = s.g2 + (size_t)t * B * 4 * D;
   const float* h2prev = s.h2 + (size_t)t * B * D;
+  float* s4t = s.s4 + (size_t)t * B * 3 * D;   // per-step [zc | sc | kc] (pre-zeroed slab)
   {  // attention-LSTM recurrent part: W_ih[:,2D:3D] h2 + W_hh h1 + hoisted terms (editnet.py:532)
-    GemmProblem p = gemm_problem(b, 4 * D, s.scratch4d, 4 * D);
+    float* pre = s.gates1 + (size_t)t * B * 4 * D;   // pre-activations, converted in place by lstm_fwd
+    GemmProblem p = gemm_problem(b, 4 * D, pre, 4 * D);
     if (t > 0) {
       gemm_add_seg(p, h2prev, D, w.al_wih + 2 * D, 3 * D + F, D);
       gemm_add_seg(p, s.X2 + (size_t)(t - 1) * B * LX2, LX2, w.al_whh, D, D);
     }
-    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D;
+    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(lstm_fwd(s.scratch4d, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
+    SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
                            s.c1 + (size_t)(t + 1) * B * D, X2t, LX2, b, D, nullptr, 0, nullptr, nullptr, 0, st));
   }
   {  // everything that consumes h1 in one grouped launch
@@ -337,6 +344,7 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     gemm_add_seg(p[4], X2t, LX2, w.cl_x2h_w, LX2, D);
     if (t > 0) gemm_add_seg(p[4], h2prev, D, w.cl_h2h_w, D, D);
     p[4].bias = w.cl_x2h_b; p[4].bias2 = w.cl_h2h_b;
+    for (int k = 0; k < 5; ++k) p[k].c_zeroed = 1;
     SET_PROPAGATE(gemm_group(kNT, p, 5, st));
   }
   {
@@ -356,16 +364,17 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
   {
     const float* ctx = s.ctx_c + (size_t)t * B * D;
     GemmProblem p[3];
-    p[0] = gemm_problem(b, D, s.s4, 3 * D);                  // context_gate[:, 2D:3D] ctx (+ h1/word parts)
+    p[0] = gemm_problem(b, D, s4t, 3 * D);                  // context_gate[:, 2D:3D] ctx (+ h1/word parts)
     gemm_add_seg(p[0], ctx, D, w.ca_gate_w + 2 * D, 3 * D, D);
     p[0].add = s2t + 2 * A; p[0].ldadd = LS2;
-    p[1] = gemm_problem(b, D, s.s4 + D, 3 * D);              // sc_affine(ctx), :380
+    p[1] = gemm_problem(b, D, s4t + D, 3 * D);              // sc_affine(ctx), :380
     gemm_add_seg(p[1], ctx, D, w.ca_sc_w, D, D); p[1].bias = w.ca_sc_b;
-    p[2] = gemm_problem(b, D, s.s4 + 2 * D, 3 * D);          // gate_cmem(sel) (+ both copy-gate biases), :281
+    p[2] = gemm_problem(b, D, s4t + 2 * D, 3 * D);          // gate_cmem(sel) (+ both copy-gate biases), :281
     gemm_add_seg(p[2], s.sel + (size_t)t * B * D, D, w.cl_gcm_w, D, D);
     p[2].bias = w.cl_gcm_b; p[2].bias2 = w.cl_gcn_b;
+    p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = 1;
     SET_PROPAGATE(gemm_group(kNT, p, 3, st));
-    SET_PROPAGATE(ctx_gate_fwd(s.s4, 3 * D, s2t + 2 * A + D, LS2, s.zst + (size_t)t * B * 3 * D, X2t + D, LX2, b, D, st));
+    SET_PROPAGATE(ctx_gate_fwd(s4t, 3 * D, s2t + 2 * A + D, LS2, s.zst + (size_t)t * B * 3 * D, X2t + D, LX2, b, D, st));
   }
   {
     GemmProblem p = gemm_problem(b, 4 * D, g2t, 4 * D);      // x2h[:, D:] [att_cap | att_img], :272
@@ -375,11 +384,11 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     SET_PROPAGATE(copy1_fwd(g2t, s.c2 + (size_t)t * B * D, s.cnew + (size_t)t * B * D, b, D, st));
   }
   {
-    GemmProblem p = gemm_problem(b, D, s.s4 + 2 * D, 3 * D);  // gate_cnew(c_new), :281
+    GemmProblem p = gemm_problem(b, D, s4t + 2 * D, 3 * D);  // gate_cnew(c_new), :281
     gemm_add_seg(p, s.cnew + (size_t)t * B * D, D, w.cl_gcn_w, D, D);
     p.beta = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(copy2_fwd(s.s4 + 2 * D, 3 * D, g2t, s.sel + (size_t)t * B * D, s.cnew + (size_t)t * B * D,
+    SET_PROPAGATE(copy2_fwd(s4t + 2 * D, 3 * D, g2t, s.sel + (size_t)t * B * D, s.cnew + (size_t)t * B * D,
                             s.kgate + (size_t)t * B * D, s.c2 + (size_t)(t + 1) * B * D,
                             s.h2 + (size_t)(t + 1) * B * D, s.h2drop + (size_t)t * B * D, b, D, c.s.train, c.seed,
                             (long)t * B * D, st));
@@ -440,7 +449,12 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     float* dS2t = s.dS2 + tb * LS2;
     float* dKt = s.dK + tb * D;
     const float* g2t = s.g2 + tb * 4 * D;
-    SET_PROPAGATE(copy2_bwd(s.dh2c, s.dh2raw + tb * D, s.dc2c, g2t, s.c2 + (tb + B) * D, s.kgate + tb * D,
+    // per-step slabs (pre-zeroed by the region memset): carries INTO step t live at index t
+    float* dX2t = s.dX2 + tb * LX2;
+    float* dctxt = s.dctx + tb * D;
+    float* dh1c_t = s.dh1c + tb * D;
+    float* dh2c_t = s.dh2c + tb * D;
+    SET_PROPAGATE(copy2_bwd(dh2c_t, s.dh2raw + tb * D, s.dc2c, g2t, s.c2 + (tb + B) * D, s.kgate + tb * D,
                             s.sel + tb * D, s.cnew + tb * D, dG2t, dKt, s.dsel, s.dcnew, b, D, c.s.train, c.seed,
                             (long)tb * D, st));
     {
@@ -451,14 +465,16 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     }
     SET_PROPAGATE(copy1_bwd(s.dcnew, g2t, s.c2 + tb * D, dG2t, s.dc2c, b, D, st));
     {
-      GemmProblem p = gemm_problem(b, LX2, s.dX2, LX2);      // d[h1 | att_cap | att_img]
+      GemmProblem p = gemm_problem(b, LX2, dX2t, LX2);      // d[h1 | att_cap | att_img]
       dx(p, dG2t, 4 * D, w.cl_x2h_w, s.t_cl_x2h, 4 * D, LX2, 0);
+      p.c_zeroed = 1;
       SET_PROPAGATE(gemm(dxm, p, st));
     }
-    SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, s.dX2 + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
+    SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, dX2t + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
                                s.dsc + tb * D, b, D, st));
     {
-      GemmProblem p = gemm_problem(b, D, s.dctx, D);
+      GemmProblem p = gemm_problem(b, D, dctxt, D);
+      p.c_zeroed = 1;
       dx(p, dS2t + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, 2 * D);
       dx(p, s.dsc + tb * D, D, w.ca_sc_w, s.t_ca_sc, D, D, 0);
       SET_PROPAGATE(gemm(dxm, p, st));
@@ -469,17 +485,17 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       a.b = b; a.P = P; a.R = R; a.D = D; a.A = A; a.F = F;
       a.att1c = s.att1c; a.s2 = s.s2 + tb * LS2; a.ld_s2 = LS2; a.cap_w = w.ca_full_w; a.mask = s.mask;
       a.prev_h = s.prev_h; a.prev_m = s.prev_m; a.alpha_c = s.alpha_c + tb * P; a.sel_idx = s.sel_idx + tb;
-      a.dctx = s.dctx; a.dsel = s.dsel; a.dprev_h = s.dprev_h; a.dprev_m = s.dprev_m; a.datt1c = s.datt1c;
+      a.dctx = dctxt; a.dsel = s.dsel; a.dprev_h = s.dprev_h; a.dprev_m = s.dprev_m; a.datt1c = s.datt1c;
       a.ds2 = dS2t; a.ld_ds2 = LS2; a.dcap_w = g.ca_full_w; a.dcap_b = g.ca_full_b;
       a.att1v = c.s.train ? s.att1 + tb * R * A : s.att1; a.vis_w = w.va_full_w; a.feats = feats;
       a.nreg = c.s.adaptive ? s.nreg : nullptr; a.alpha_v = s.alpha_v + tb * R;
-      a.datt_img = s.dX2 + 2 * D; a.ld_dimg = LX2;
+      a.datt_img = dX2t + 2 * D; a.ld_dimg = LX2;
       a.datt1v = c.s.train ? s.datt1 + tb * R * A : s.datt1; a.datt1v_accum = c.s.train ? 0 : 1;
       a.dvis_w = g.va_full_w; a.dvis_b = g.va_full_b;
       SET_PROPAGATE(attention_bwd(a, st));
     }
     {
-      GemmProblem p = gemm_problem(b, D, s.dX2, LX2);        // dh1 += every consumer of h1
+      GemmProblem p = gemm_problem(b, D, dX2t, LX2);        // dh1 += every consumer of h1
       dx(p, dS2t, LS2, w.ca_dec_w, s.t_ca_dec, A, D, 0);
       dx(p, dS2t + A, LS2, w.va_dec_w, s.t_va_dec, A, D, 0);
       dx(p, dS2t + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, D);
@@ -487,12 +503,13 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       p.beta = 1;
       SET_PROPAGATE(gemm(dxm, p, st));
     }
-    SET_PROPAGATE(lstm_bwd(s.gates1 + tb * 4 * D, s.c1 + tb * D, s.c1 + (tb + B) * D, s.dX2, LX2, s.dh1c, s.dc1c,
+    SET_PROPAGATE(lstm_bwd(s.gates1 + tb * 4 * D, s.c1 + tb * D, s.c1 + (tb + B) * D, dX2t, LX2, dh1c_t, s.dc1c,
                            dG1t, b, D, st));
     if (t > 0) {
       GemmProblem p[2];
-      p[0] = gemm_problem(b, D, s.dh1c, D); dx(p[0], dG1t, 4 * D, w.al_whh, s.t_al_whh, 4 * D, D, 0);
-      p[1] = gemm_problem(b, D, s.dh2c, D);
+      p[0] = gemm_problem(b, D, dh1c_t - (size_t)B * D, D); dx(p[0], dG1t, 4 * D, w.al_whh, s.t_al_whh, 4 * D, D, 0);
+      p[1] = gemm_problem(b, D, dh2c_t - (size_t)B * D, D);
+      p[0].c_zeroed = p[1].c_zeroed = 1;
       dx(p[1], dG1t, 4 * D, w.al_wih, s.t_al_wih, 4 * D, 3 * D + F, 2 * D);
       dx(p[1], dG2t, 4 * D, w.cl_h2h_w, s.t_cl_h2h, 4 * D, D, 0);
       SET_PROPAGATE(gemm_group(dxm, p, 2, st));
@@ -648,11 +665,12 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   }
   for (int t = P - 1; t >= 0; --t) {
     const size_t tb = (size_t)t * B;
-    SET_PROPAGATE(enc_lstm_bwd(s.enc_gates + tb * 4 * D, s.enc_c + tb * D, s.enc_c + (tb + B) * D, s.dh_run,
+    SET_PROPAGATE(enc_lstm_bwd(s.enc_gates + tb * 4 * D, s.enc_c + tb * D, s.enc_c + (tb + B) * D, s.dh_run + tb * D,
                                s.dc_run, s.dprev_h, s.dprev_m, (long)P * D, s.dh_last, prev_len, t,
                                s.denc_g + tb * 4 * D, B, D, st));
     if (t > 0) {
-      GemmProblem p = gemm_problem(B, D, s.dh_run, D);
+      GemmProblem p = gemm_problem(B, D, s.dh_run + (tb - B) * D, D);
+      p.c_zeroed = 1;
       dx(p, s.denc_g + tb * 4 * D, 4 * D, w.enc_h2h_w, s.t_enc_h2h, 4 * D, D, 0);
       SET_PROPAGATE(gemm(dxm, p, st));
     }

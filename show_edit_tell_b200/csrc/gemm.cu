@@ -212,14 +212,15 @@ long long g_tc_launches = 0, g_simt_launches = 0;
 int gemm_group(int mode, const GemmProblem* probs_in, int n, cudaStream_t stream) {
   SET_REQUIRE(n >= 1 && n <= 8, "1..8 problems per group");
   GemmProblem probs[8];
+  bool taken[8] = {false, false, false, false, false, false, false, false};
+  if (g_backend == 0) {
+    SET_PROPAGATE(gemm_tc_try_group(mode, probs_in, n, taken, stream));
+    for (int i = 0; i < n; ++i)
+      if (taken[i]) { ++g_tc_launches; break; }
+  }
   int kept = 0;
   for (int i = 0; i < n; ++i) {
-    if (probs_in[i].M <= 0 || probs_in[i].N <= 0) continue;
-    if (g_backend == 0) {
-      const int r = gemm_tc_try(mode, probs_in[i], stream);
-      if (r == SET_OK) { ++g_tc_launches; continue; }
-      if (r != -1) return r;
-    }
+    if (probs_in[i].M <= 0 || probs_in[i].N <= 0 || taken[i]) continue;
     probs[kept++] = probs_in[i];
   }
   n = kept;

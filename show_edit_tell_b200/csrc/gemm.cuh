@@ -31,6 +31,7 @@ struct GemmProblem {
   int c_inner; long c_ld_inner;          // two-level C rows
   const int* c_row_len; int c_valid_inner;  // invalid C rows are not written
   int beta;                              // 1: C += result
+  int c_zeroed;                          // caller guarantees C is all-zero (lets split-K skip its memset)
   int act;                               // 0 none, 1 relu, 2 tanh
 };
 
@@ -52,8 +53,8 @@ inline void gemm_add_seg(GemmProblem& p, const float* A, long lda, const float* 
   s.A = A; s.lda = lda; s.B = B; s.ldb = ldb; s.K = K;
 }
 
-// tensor-core path (gemm_tc.cu): SET_OK if launched, -1 if the problem is not eligible
-int gemm_tc_try(int mode, const GemmProblem& p, cudaStream_t stream);
+// tensor-core path (gemm_tc.cu): launches the eligible problems of a group in one grid
+int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cudaStream_t stream);
 void gemm_tc_set_trace(unsigned long long* buf);
 extern int g_backend;
 extern long long g_tc_launches, g_simt_launches;

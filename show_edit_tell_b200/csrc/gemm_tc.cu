@@ -132,9 +132,18 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+struct TcGroup {
+  int n;
+  int cta_start[9];        // first CTA of each problem (tiles * split_k each)
+  TcParams p[8];
+};
+
 template <int QN>
-__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_constant__ TcParams prm) {
+__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_constant__ TcGroup grp) {
   using Cfg = TcCfg<QN>;
+  int pi = 0;
+  while (pi + 1 < grp.n && (int)blockIdx.x >= grp.cta_start[pi + 1]) ++pi;
+  const TcParams& prm = grp.p[pi];
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   if (threadIdx.x == 64) TC_STAMP(0);
 
   // tile / split decode
-  int bid = blockIdx.x;
+  int bid = blockIdx.x - grp.cta_start[pi];
   const int ks = bid % prm.split_k; bid /= prm.split_k;
   const int qt = bid % prm.tiles_q;
   const int pt = bid / prm.tiles_q;
@@ -422,26 +431,22 @@ bool aligned_ok(const float* p, long ld) { return (reinterpret_cast<uintptr_t>(p
 
 }  // namespace
 
-// Returns SET_OK if launched, -1 if this problem is not eligible for the tensor-core path (caller
-// falls back to the CUDA-core kernel), or an error code.
-int gemm_tc_try(int mode, const GemmProblem& g, cudaStream_t stream) {
-  std::call_once(g_tc_once, tc_init);
-  if (!g_tc_ready) return -1;
-  if (g.nseg < 1 || g.M <= 0 || g.N <= 0) return -1;
+// Fills `prm` for one problem; returns false if the problem is not eligible for the tensor-core path
+// (caller falls back to the CUDA-core kernel).  `QN` is the Q-tile width chosen for the whole group.
+static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
+  if (g.nseg < 1 || g.M <= 0 || g.N <= 0) return false;
   // MN-major operands (the NN / TN forms) are wired through the kernel but read back as zeros on
   // sm_100a with these descriptors (tools/debug_tc2.py) -- until that is understood only the
   // K-major/K-major (NT) form runs on tensor cores; callers present NN/TN work in NT form on
   // transposed copies (editnet.cu backward_core) or fall back to the CUDA-core kernel.
-  if (mode != kNT && getenv("SET_TC_ALLOW_MN") == nullptr) return -1;
-  if (g.a_inner > 0 || g.a_row_len) return -1;            // two-level / masked A rows stay on the CUDA-core path
+  if (mode != kNT && getenv("SET_TC_ALLOW_MN") == nullptr) return false;
+  if (g.a_inner > 0 || g.a_row_len) return false;         // two-level / masked A rows stay on the CUDA-core path
   long ktot = 0;
   for (int s = 0; s < g.nseg; ++s) {
-    if (!aligned_ok(g.seg[s].A, g.seg[s].lda) || !aligned_ok(g.seg[s].B, g.seg[s].ldb)) return -1;
+    if (!aligned_ok(g.seg[s].A, g.seg[s].lda) || !aligned_ok(g.seg[s].B, g.seg[s].ldb)) return false;
     ktot += g.seg[s].K;
   }
-  if (ktot < 64) return -1;
-
-  TcParams prm;
+  if (ktot < 64) return false;
   memset(&prm, 0, sizeof(prm));
   // operand roles: the A-side (M rows) and the B-side (N rows) of the logical GEMM
   //   kNT: A[m][k] K-major,   B[n][k] K-major
@@ -449,10 +454,9 @@ int gemm_tc_try(int mode, const GemmProblem& g, cudaStream_t stream) {
   //   kTN: A[k][m] MN-major,  B[k][n] MN-major
   const int a_mn = (mode == kTN), b_mn = (mode != kNT);
   // skinny M: weights (B side, N rows) take the 128-row P role
-  const bool swap = (g.M <= 128 && g.N > g.M);
+  const bool swap = (g.M <= QN && g.N > g.M);
   const int Pr = swap ? g.N : g.M, Qr = swap ? g.M : g.N;
-  const int QN = (Qr <= 64) ? 64 : 128;
-  if (swap && (g.c_inner > 0)) return -1;
+  if (swap && (g.c_inner > 0)) return false;
   prm.swap = swap; prm.Pr = Pr; prm.Qr = Qr;
   prm.p_mn = swap ? b_mn : a_mn;
   prm.q_mn = swap ? a_mn : b_mn;
@@ -467,36 +471,72 @@ int gemm_tc_try(int mode, const GemmProblem& g, cudaStream_t stream) {
     else ok = make_map(&prm.mapP[s], Pp, sg.K, Pr, Pld, 32, kBlockK);
     if (!prm.q_mn) ok = ok && make_map(&prm.mapQ[s], Qp, Qr, sg.K, Qld, kBlockK, QN);
     else ok = ok && make_map(&prm.mapQ[s], Qp, sg.K, Qr, Qld, 32, kBlockK);
-    if (!ok) return -1;
+    if (!ok) return false;
   }
   prm.tiles_p = (Pr + kTileP - 1) / kTileP;
   prm.tiles_q = (Qr + QN - 1) / QN;
-  long nkb = 0;
-  for (int s = 0; s < g.nseg; ++s) nkb += (g.seg[s].K + kBlockK - 1) / kBlockK;
-  int split = 1;
-  const long tiles = (long)prm.tiles_p * prm.tiles_q;
-  if (g.act == 0 && tiles < 148) {
-    split = (int)(148 / tiles);
-    const int max_split = (int)(nkb / 4 > 0 ? nkb / 4 : 1);
-    if (split > max_split) split = max_split;
-    if (split > 16) split = 16;
-    if (split < 1) split = 1;
-  }
-  prm.split_k = split;
+  prm.split_k = 1;
   prm.C = g.C; prm.ldc = g.ldc; prm.c_inner = g.c_inner; prm.c_ld_inner = g.c_ld_inner;
   prm.c_row_len = g.c_row_len; prm.c_valid_inner = g.c_valid_inner > 0 ? g.c_valid_inner : 1;
   prm.bias = g.bias; prm.bias2 = g.bias2; prm.add = g.add; prm.ldadd = g.ldadd; prm.add_mod = g.add_mod;
   prm.beta = g.beta; prm.act = g.act;
   { const char* e = getenv("SET_TC_IDESC_XOR"); prm.idesc_xor = e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }
   prm.trace = g_tc_trace;
-  if (split > 1 && !g.beta) {
-    // partial sums meet in global atomics: clear the destination first
-    if (g.c_inner > 0 || g.c_row_len) return -1;
-    SET_CHECK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, stream));
+  return true;
+}
+
+// Launches every eligible problem of the group in ONE grid (taken[i] = true); the others are left to
+// the CUDA-core kernel.  Independent GEMMs of one phase of the decode step (everything that consumes
+// h1, say) thereby stream their weights concurrently instead of paying a launch each.
+int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cudaStream_t stream) {
+  for (int i = 0; i < n; ++i) taken[i] = false;
+  std::call_once(g_tc_once, tc_init);
+  if (!g_tc_ready) return SET_OK;
+  // one Q-tile width per launch: 64 if every problem's small side fits, else 128
+  int QN = 64;
+  for (int i = 0; i < n; ++i) {
+    const GemmProblem& g = probs[i];
+    if (g.M <= 0 || g.N <= 0) continue;
+    const int small = g.M < g.N ? g.M : g.N;
+    if (small > 64) QN = 128;
   }
-  const int grid = (int)(tiles * split);
-  if (QN == 64) gemm_tc_kernel<64><<<grid, kThreadsTc, TcCfg<64>::kSmemBytes, stream>>>(prm);
-  else gemm_tc_kernel<128><<<grid, kThreadsTc, TcCfg<128>::kSmemBytes, stream>>>(prm);
+  static TcGroup grp;     // host staging (launch copies it); calls are serialised by the caller's stream use
+  grp.n = 0;
+  long tiles_total = 0;
+  int idx[8];
+  for (int i = 0; i < n; ++i) {
+    if (probs[i].M <= 0 || probs[i].N <= 0) { taken[i] = true; continue; }
+    if (!tc_plan(mode, probs[i], QN, grp.p[grp.n])) continue;
+    idx[grp.n] = i;
+    tiles_total += (long)grp.p[grp.n].tiles_p * grp.p[grp.n].tiles_q;
+    ++grp.n;
+  }
+  if (grp.n == 0) return SET_OK;
+  // split-K: spread the group over ~all SMs (partials meet in global reductions)
+  int cta = 0;
+  for (int k = 0; k < grp.n; ++k) {
+    TcParams& prm = grp.p[k];
+    const GemmProblem& g = probs[idx[k]];
+    long nkb = 0;
+    for (int s = 0; s < g.nseg; ++s) nkb += (g.seg[s].K + kBlockK - 1) / kBlockK;
+    int split = 1;
+    if (g.act == 0 && tiles_total < 148 && !(g.c_inner > 0 || g.c_row_len)) {
+      split = (int)(148 / tiles_total);
+      const int max_split = (int)(nkb / 4 > 0 ? nkb / 4 : 1);
+      if (split > max_split) split = max_split;
+      if (split > 16) split = 16;
+      if (split < 1) split = 1;
+    }
+    prm.split_k = split;
+    if (split > 1 && !g.beta && !g.c_zeroed)   // partial sums are reduced into C: it must start at zero
+      SET_CHECK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, stream));
+    grp.cta_start[k] = cta;
+    cta += prm.tiles_p * prm.tiles_q * split;
+    taken[idx[k]] = true;
+  }
+  grp.cta_start[grp.n] = cta;
+  if (QN == 64) gemm_tc_kernel<64><<<cta, kThreadsTc, TcCfg<64>::kSmemBytes, stream>>>(grp);
+  else gemm_tc_kernel<128><<<cta, kThreadsTc, TcCfg<128>::kSmemBytes, stream>>>(grp);
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
   return SET_OK;
