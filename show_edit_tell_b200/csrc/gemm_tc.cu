@@ -521,11 +521,14 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     for (int s = 0; s < g.nseg; ++s) nkb += (g.seg[s].K + kBlockK - 1) / kBlockK;
     int split = 1;
     if (g.act == 0 && tiles_total < 148 && !(g.c_inner > 0 || g.c_row_len)) {
+      // fill one wave of the 148 SMs (a second wave would repeat every CTA's fixed prologue/epilogue)
       split = (int)(148 / tiles_total);
       const int max_split = (int)(nkb / 4 > 0 ? nkb / 4 : 1);
       if (split > max_split) split = max_split;
       if (split > 16) split = 16;
       if (split < 1) split = 1;
+      // a long-K problem that fills only ~half the machine: three partials over two waves is ~1.5x faster
+      if (split == 1 && tiles_total * 3 <= 2 * 148 && nkb >= 96) split = 3;
     }
     prm.split_k = split;
     if (split > 1 && !g.beta && !g.c_zeroed)   // partial sums are reduced into C: it must start at zero
