@@ -90,6 +90,15 @@ SET_API int set_version(void);
  * by set_editnet_rollout for this shape. */
 SET_API size_t set_editnet_workspace_bytes(const SetDims* dims, const SetSeqShape* shape);
 
+/* Previous-caption encoder alone: replaces CaptionEncoderC.forward, editnet.py:319-348 (rows in caller
+ * order; the reference's internal sort/unsort is unobservable).  Outputs (any may be NULL):
+ * hidden_states / memory_states [B,P,D] (zero beyond each row's length), final_hidden [B,D], mask [B,P].
+ * shape: B, Wp, P, train are used (R = T = 1 is fine). */
+SET_API int set_editnet_encode(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                       const int64_t* seq, const int64_t* seq_len, uint64_t seed, float* hidden_states,
+                       float* memory_states, float* final_hidden, float* mask, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Teacher-forced forward: replaces DecoderC.forward, editnet.py:479-548 (use_ss=False)
  * and, with shape->adaptive, adaptive_features/editnet_adaptive.py:489-562.
  *   feats            [B,R,F]   image_features[sort_ind]

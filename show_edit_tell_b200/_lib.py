@@ -129,6 +129,8 @@ _SIGS = {
     "set_editnet_workspace_bytes": (C.c_size_t, [C.POINTER(SetDims), C.POINTER(SetSeqShape)]),
     "set_editnet_workspace_lookup": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.c_char_p,
                                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "set_editnet_encode": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams), _P, _P,
+                                     C.c_uint64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "set_editnet_xe_forward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),
                                          _P, _P, _P, C.POINTER(C.c_int), _P, _P, C.c_uint64, _P, _P, C.c_size_t, _P]),
     "set_editnet_xe_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),

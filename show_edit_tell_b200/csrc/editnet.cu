@@ -198,9 +198,8 @@ int profile_mark(int idx, cudaStream_t st) {
 
 // --------------------------------------------------------------------- shared prologue
 // caption encoder (editnet.py:319-348), image mean (:503), hoisted time-invariant projections
-int prepare_common(Ctx& c, const float* feats, const float* image_mean_in, const int64_t* prev,
-                   const int64_t* prev_len) {
-  const int B = c.s.B, P = c.s.P, T = c.s.T, R = c.s.R, D = c.d.D, A = c.d.A, F = c.d.F;
+int encode_prev(Ctx& c, const int64_t* prev, const int64_t* prev_len) {
+  const int B = c.s.B, P = c.s.P, T = c.s.T, D = c.d.D, A = c.d.A;
   const SetEditNetParams& w = *c.w;
   Ws& s = c.ws;
   cudaStream_t st = c.st;
@@ -242,6 +241,16 @@ int prepare_common(Ctx& c, const float* feats, const float* image_mean_in, const
     p[1].bias = w.ca_feat_b;
     SET_PROPAGATE(gemm(kNT, p[1], st));
   }
+  return SET_OK;
+}
+
+int prepare_common(Ctx& c, const float* feats, const float* image_mean_in, const int64_t* prev,
+                   const int64_t* prev_len) {
+  const int B = c.s.B, T = c.s.T, R = c.s.R, D = c.d.D, A = c.d.A, F = c.d.F;
+  const SetEditNetParams& w = *c.w;
+  Ws& s = c.ws;
+  cudaStream_t st = c.st;
+  SET_PROPAGATE(encode_prev(c, prev, prev_len));
   // --- image side
   if (c.s.adaptive) {
     SET_REQUIRE(image_mean_in != nullptr, "adaptive needs image_mean");
@@ -716,6 +725,24 @@ int set_editnet_workspace_lookup(const SetDims* dims, const SetSeqShape* shape, 
     if (e.name == name) { *offset = e.off; *bytes = e.bytes; return SET_OK; }
   set_record_error("unknown workspace buffer name");
   return SET_ERR_ARG;
+}
+
+int set_editnet_encode(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w, const int64_t* seq,
+                       const int64_t* seq_len, uint64_t seed, float* hidden_states, float* memory_states,
+                       float* final_hidden, float* mask, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
+  SET_REQUIRE(seq && seq_len, "null input");
+  SET_PROPAGATE(encode_prev(c, seq, seq_len));
+  const size_t B = shape->B, P = shape->P, D = dims->D;
+  if (hidden_states)
+    SET_CHECK_CUDA(cudaMemcpyAsync(hidden_states, c.ws.prev_h, sizeof(float) * B * P * D, cudaMemcpyDeviceToDevice, c.st));
+  if (memory_states)
+    SET_CHECK_CUDA(cudaMemcpyAsync(memory_states, c.ws.prev_m, sizeof(float) * B * P * D, cudaMemcpyDeviceToDevice, c.st));
+  if (final_hidden)
+    SET_CHECK_CUDA(cudaMemcpyAsync(final_hidden, c.ws.fh, sizeof(float) * B * D, cudaMemcpyDeviceToDevice, c.st));
+  if (mask) SET_CHECK_CUDA(cudaMemcpyAsync(mask, c.ws.mask, sizeof(float) * B * P, cudaMemcpyDeviceToDevice, c.st));
+  return SET_OK;
 }
 
 int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,

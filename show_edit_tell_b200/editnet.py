@@ -371,6 +371,29 @@ class EditNetBase(nn.Module):
             return _RolloutFunction.apply(self, call, *self._ordered_params())
         return self._rollout_raw(call)
 
+    def encode(self, seq, seq_len, seed=None):
+        """CaptionEncoderC.forward (editnet.py:319-348) on its own, no autograd:
+        -> (hidden_states (B,P',D), memory_states (B,P',D), final_hidden (B,D), mask (B,P'))"""
+        self._require_cuda(seq)
+        self.flatten_parameters()
+        seq = seq.contiguous()
+        lens = seq_len.contiguous().view(-1)
+        B, Wp = seq.shape
+        P = int(lens.max().item())
+        dims = self._dims()
+        shape = SetSeqShape(B, 1, 0, Wp, P, 1, int(self.training), 0)
+        nbytes = _lib.lib().set_editnet_workspace_bytes(C.byref(dims), C.byref(shape))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=seq.device)
+        D = self.decoder_dim
+        h = torch.empty(B, P, D, device=seq.device)
+        m = torch.empty(B, P, D, device=seq.device)
+        fh = torch.empty(B, D, device=seq.device)
+        mask = torch.empty(B, P, device=seq.device)
+        sd = (_draw_seed() if seed is None else seed) if self.training else 0
+        check(_lib.lib().set_editnet_encode(C.byref(dims), C.byref(shape), C.byref(self._struct), ptr(seq), ptr(lens), sd,
+                                            ptr(h), ptr(m), ptr(fh), ptr(mask), ptr(ws), ws.numel(), _stream()))
+        return h, m, fh, mask
+
     # debugging / tests: a named workspace buffer of the last call as a float tensor
     def workspace_tensor(self, name, dtype=torch.float32):
         call = self._last_call

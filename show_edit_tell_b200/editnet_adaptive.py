@@ -20,11 +20,8 @@ class DecoderC(EditNetBase):
         idx = torch.tensor(call.decode_lengths, device=h2.device)
         last_hidden = h2[idx, torch.arange(B, device=h2.device)].clone()
         # gd_final_hidden: encoder run on the ground-truth caption (:516) -- a second encoder pass
-        gd_final_hidden = None  # TODO(encoder entry point): second encoder pass on the GT caption
+        # gd_final_hidden: the encoder run on the ground-truth caption (:516).  No autograd edge: it only
+        # matters for the optional MSE term, which the reference disables (use_mse=False, :781).
+        with torch.no_grad():
+            gd_final_hidden = self.encode(call.caps, idx + 1)[2]
         return pred, call.caps, call.decode_lengths, call.sort_ind, gd_final_hidden, last_hidden
-
-    def encode_final_hidden(self, seq, seq_len):
-        """final_hidden of the caption encoder for arbitrary token rows (no grad): a zero-step
-        rollout call runs exactly the encoder prologue."""
-        raise NotImplementedError("gd_final_hidden (only consumed when use_mse=True, which the reference "
-                                  "disables at editnet_adaptive.py:781) is not built yet")

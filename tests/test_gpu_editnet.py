@@ -351,3 +351,27 @@ def test_trainer_step_matches_oracle_step(small_sd, small_cfg):
         # Adam's first update is lr*g/(|g|+eps): only well-conditioned where |g| >> eps
         big = ref_grads[k].abs() * min(1.0, 0.25 / float(total)) > 1e-6
         assert ((got - p).abs() * big).max() < 5e-6, k
+
+
+def test_caption_encoder_entry_and_adaptive_six_tuple(small_sd, small_cfg):
+    _lib, editnet, editnet_rl, editnet_adaptive, trainmod, U = _imports()
+    c = small_cfg
+    g = load_npz("editnet_adaptive_eval")
+    mod, _ = U.build_module(editnet_adaptive.DecoderC, small_sd, c["V"], c["D"], c["A"], c["Fdim"])
+    mod.eval()
+    h, m, fh, mask = mod.encode(g["prev"].cuda(), g["prev_len"].cuda())
+    rh, rm, rfh, rmask = EO.caption_encoder(small_sd, g["prev"], g["prev_len"])
+    for a, b in ((h, rh), (m, rm), (fh, rfh), (mask, rmask)):
+        assert (a.cpu() - b).abs().max() < 1e-5
+    args = _cuda(g, XE_KEYS)
+    with torch.no_grad():
+        out = mod(args[0], g["image_mean"].cuda(), *args[1:], False, 0.0)
+    assert len(out) == 6
+    pred, caps_sorted, dl, sort_ind, gd_fh, last_h = out
+    # gd_final_hidden = encoder(final) of the sorted GT captions (editnet_adaptive.py:516)
+    ref_gd = EO.caption_encoder(small_sd, caps_sorted.cpu(), torch.tensor(dl) + 1)[2]
+    assert (gd_fh.cpu() - ref_gd).abs().max() < 1e-5
+    # decoder_last_hidden = h2 at each row's last decoded step (:560): fc(last_h) reproduces the last logits
+    last_logits = torch.stack([pred[i, dl[i] - 1] for i in range(len(dl))]).cpu()
+    w, b = small_sd["fc.weight"], small_sd["fc.bias"]
+    assert (last_h.cpu() @ w.t() + b - last_logits).abs().max() < 1e-4
