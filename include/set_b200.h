@@ -99,6 +99,20 @@ SET_API int set_editnet_encode(const SetDims* dims, const SetSeqShape* shape, co
                        float* memory_states, float* final_hidden, float* mask, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* One decode step on explicit state -- what beam search needs (evaluate(), editnet.py:639-653 calls the
+ * cells one by one on k <= beam_size rows; here the whole step is one call).  set_editnet_step_begin runs
+ * the per-image/per-caption precomputation once (encoder, attention projections) for B rows into the
+ * workspace; set_editnet_step then advances the first `rows` rows: embeds `tokens`, updates
+ * (h1,c1,h2,c2) [rows,D] IN PLACE and writes the vocabulary scores fc(h2) [rows,V].  Rows keep their
+ * identity across steps (the reference's beams share one image, so re-ordering beams only permutes the
+ * caller's state tensors).  shape->T must be 2 and shape->train 0. */
+SET_API int set_editnet_step_begin(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                           const float* feats, const float* image_mean, const int64_t* prev,
+                           const int64_t* prev_len, void* workspace, size_t workspace_bytes, void* stream);
+SET_API int set_editnet_step(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                     const float* feats, const int64_t* tokens, int rows, float* h1, float* c1, float* h2,
+                     float* c2, float* scores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Teacher-forced forward: replaces DecoderC.forward, editnet.py:479-548 (use_ss=False)
  * and, with shape->adaptive, adaptive_features/editnet_adaptive.py:489-562.
  *   feats            [B,R,F]   image_features[sort_ind]

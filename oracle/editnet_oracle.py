@@ -330,3 +330,51 @@ def init_state_dict(V, D=1024, C=1024, E=1024, A=512, Fdim=2048, seed=0, dtype=t
     linear("copy_lstm.gate_cmem", D, D, k)
     linear("fc", V, D)
     return sd
+
+
+def beam_search(sd, word_map, feats, prev, prev_len, beam_size=3, max_steps=50):
+    """evaluate()'s search loop, editnet.py:608-719, for one image (feats (1,R,F), prev (1,Wp),
+    prev_len (1,1)), eval mode.  `top_k_words / vocab_size` (:666) is true division on torch >= 1.5 and
+    crashes (SURVEY Appendix D); the reference's intent (torch 1.2 integer division) is restated as //."""
+    k = beam_size
+    V, D = sd["fc.weight"].shape
+    enc = caption_encoder(sd, prev, prev_len)                                              # :613
+    feats_k = feats.expand(k, -1, -1)                                                       # :616
+    enc_k = tuple(x.expand(k, *x.shape[1:]) for x in enc)                                   # :617-621
+    words = torch.full((k,), word_map["<start>"], dtype=torch.long)
+    seqs = words.unsqueeze(1)
+    top = torch.zeros(k, 1)
+    done_seqs, done_scores = [], []
+    st = tuple(feats.new_zeros(k, D) for _ in range(4))
+    step = 1
+    while True:
+        n = words.shape[0]
+        e = embed(sd, words)
+        st, _ = decoder_step(sd, e, st, tuple(x[:n] for x in enc_k), feats_k[:n], feats_k[:n].mean(1))
+        scores = F.log_softmax(_lin(sd, "fc", st[2]), dim=1)                                # :653-654
+        scores = top.expand_as(scores) + scores
+        if step == 1:
+            top_s, top_w = scores[0].topk(k, 0, True, True)
+        else:
+            top_s, top_w = scores.view(-1).topk(k, 0, True, True)
+        pi, ni = top_w // V, top_w % V
+        seqs = torch.cat([seqs[pi], ni.unsqueeze(1)], 1)
+        inc = [i for i, w in enumerate(ni.tolist()) if w != word_map["<end>"]]
+        com = [i for i in range(len(ni)) if i not in inc]
+        if com:
+            done_seqs.extend(seqs[com].tolist())
+            done_scores.extend(top_s[com].tolist())
+        k -= len(com)
+        if k == 0:
+            break
+        seqs = seqs[inc]
+        st = tuple(x[pi[inc]] for x in st)
+        top = top_s[inc].unsqueeze(1)
+        words = ni[inc]
+        if step > max_steps:
+            break
+        step += 1
+    if not done_scores:
+        return seqs[0].tolist(), float(top[0])
+    i = done_scores.index(max(done_scores))
+    return done_seqs[i], done_scores[i]

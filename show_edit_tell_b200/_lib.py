@@ -131,6 +131,10 @@ _SIGS = {
                                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "set_editnet_encode": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams), _P, _P,
                                      C.c_uint64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "set_editnet_step_begin": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams), _P, _P,
+                                         _P, _P, _P, C.c_size_t, _P]),
+    "set_editnet_step": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams), _P, _P,
+                                   C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "set_editnet_xe_forward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),
                                          _P, _P, _P, C.POINTER(C.c_int), _P, _P, C.c_uint64, _P, _P, C.c_size_t, _P]),
     "set_editnet_xe_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),

@@ -43,6 +43,7 @@ struct Ctx {
   cudaStream_t st;
   uint64_t seed;
   int LS2, LX2;
+  int fresh = 1;   // 1: GEMM output slabs were zeroed by the region memset of this call (split-K skips memsets)
 };
 
 void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
@@ -222,7 +223,7 @@ int encode_prev(Ctx& c, const int64_t* prev, const int64_t* prev_len) {
     float* pre = s.enc_gates + (size_t)t * B * 4 * D;   // pre-activations, converted in place by lstm_fwd
     GemmProblem p = gemm_problem(B, 4 * D, pre, 4 * D);
     if (t > 0) gemm_add_seg(p, s.enc_h + (size_t)t * B * D, D, w.enc_h2h_w, D, D);
-    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = 1;
+    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh;
     SET_PROPAGATE(gemm(kNT, p, st));
     SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
                            s.enc_gates + (size_t)t * B * 4 * D, s.enc_c + (size_t)(t + 1) * B * D,
@@ -309,7 +310,7 @@ int project_words(Ctx& c, int t0, int nt) {
   p[2] = gemm_problem(nt * B, D, s.tw + r0 * D, D);
   gemm_add_seg(p[2], s.emb_all + r0 * D, D, w.ca_tc_w, 2 * D, D);
   p[2].bias = w.ca_tc_b;
-  p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = 1;
+  p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = c.fresh;
   return gemm_group(kNT, p, 3, c.st);
 }
 
@@ -332,7 +333,7 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
       gemm_add_seg(p, h2prev, D, w.al_wih + 2 * D, 3 * D + F, D);
       gemm_add_seg(p, s.X2 + (size_t)(t - 1) * B * LX2, LX2, w.al_whh, D, D);
     }
-    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = 1;
+    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh;
     SET_PROPAGATE(gemm(kNT, p, st));
     SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
                            s.c1 + (size_t)(t + 1) * B * D, X2t, LX2, b, D, nullptr, 0, nullptr, nullptr, 0, st));
@@ -353,7 +354,7 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     gemm_add_seg(p[4], X2t, LX2, w.cl_x2h_w, LX2, D);
     if (t > 0) gemm_add_seg(p[4], h2prev, D, w.cl_h2h_w, D, D);
     p[4].bias = w.cl_x2h_b; p[4].bias2 = w.cl_h2h_b;
-    for (int k = 0; k < 5; ++k) p[k].c_zeroed = 1;
+    for (int k = 0; k < 5; ++k) p[k].c_zeroed = c.fresh;
     SET_PROPAGATE(gemm_group(kNT, p, 5, st));
   }
   {
@@ -381,7 +382,7 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     p[2] = gemm_problem(b, D, s4t + 2 * D, 3 * D);          // gate_cmem(sel) (+ both copy-gate biases), :281
     gemm_add_seg(p[2], s.sel + (size_t)t * B * D, D, w.cl_gcm_w, D, D);
     p[2].bias = w.cl_gcm_b; p[2].bias2 = w.cl_gcn_b;
-    p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = 1;
+    p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = c.fresh;
     SET_PROPAGATE(gemm_group(kNT, p, 3, st));
     SET_PROPAGATE(ctx_gate_fwd(s4t, 3 * D, s2t + 2 * A + D, LS2, s.zst + (size_t)t * B * 3 * D, X2t + D, LX2, b, D, st));
   }
@@ -476,14 +477,14 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     {
       GemmProblem p = gemm_problem(b, LX2, dX2t, LX2);      // d[h1 | att_cap | att_img]
       dx(p, dG2t, 4 * D, w.cl_x2h_w, s.t_cl_x2h, 4 * D, LX2, 0);
-      p.c_zeroed = 1;
+      p.c_zeroed = c.fresh;
       SET_PROPAGATE(gemm(dxm, p, st));
     }
     SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, dX2t + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
                                s.dsc + tb * D, b, D, st));
     {
       GemmProblem p = gemm_problem(b, D, dctxt, D);
-      p.c_zeroed = 1;
+      p.c_zeroed = c.fresh;
       dx(p, dS2t + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, 2 * D);
       dx(p, s.dsc + tb * D, D, w.ca_sc_w, s.t_ca_sc, D, D, 0);
       SET_PROPAGATE(gemm(dxm, p, st));
@@ -518,7 +519,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       GemmProblem p[2];
       p[0] = gemm_problem(b, D, dh1c_t - (size_t)B * D, D); dx(p[0], dG1t, 4 * D, w.al_whh, s.t_al_whh, 4 * D, D, 0);
       p[1] = gemm_problem(b, D, dh2c_t - (size_t)B * D, D);
-      p[0].c_zeroed = p[1].c_zeroed = 1;
+      p[0].c_zeroed = p[1].c_zeroed = c.fresh;
       dx(p[1], dG1t, 4 * D, w.al_wih, s.t_al_wih, 4 * D, 3 * D + F, 2 * D);
       dx(p[1], dG2t, 4 * D, w.cl_h2h_w, s.t_cl_h2h, 4 * D, D, 0);
       SET_PROPAGATE(gemm_group(dxm, p, 2, st));
@@ -679,7 +680,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
                                s.denc_g + tb * 4 * D, B, D, st));
     if (t > 0) {
       GemmProblem p = gemm_problem(B, D, s.dh_run + (tb - B) * D, D);
-      p.c_zeroed = 1;
+      p.c_zeroed = c.fresh;
       dx(p, s.denc_g + tb * 4 * D, 4 * D, w.enc_h2h_w, s.t_enc_h2h, 4 * D, D, 0);
       SET_PROPAGATE(gemm(dxm, p, st));
     }
@@ -742,6 +743,47 @@ int set_editnet_encode(const SetDims* dims, const SetSeqShape* shape, const SetE
   if (final_hidden)
     SET_CHECK_CUDA(cudaMemcpyAsync(final_hidden, c.ws.fh, sizeof(float) * B * D, cudaMemcpyDeviceToDevice, c.st));
   if (mask) SET_CHECK_CUDA(cudaMemcpyAsync(mask, c.ws.mask, sizeof(float) * B * P, cudaMemcpyDeviceToDevice, c.st));
+  return SET_OK;
+}
+
+int set_editnet_step_begin(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                           const float* feats, const float* image_mean, const int64_t* prev,
+                           const int64_t* prev_len, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, 0, stream));
+  SET_REQUIRE(shape->T == 2 && shape->train == 0, "step sessions use T == 2, eval mode");
+  SET_REQUIRE(feats && prev && prev_len, "null input");
+  return prepare_common(c, feats, image_mean, prev, prev_len);
+}
+
+int set_editnet_step(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w, const float* feats,
+                     const int64_t* tokens, int rows, float* h1, float* c1, float* h2, float* c2, float* scores,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx c;
+  SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, 0, stream));
+  SET_REQUIRE(shape->T == 2 && shape->train == 0, "step sessions use T == 2, eval mode");
+  SET_REQUIRE(feats && tokens && h1 && c1 && h2 && c2 && scores && rows >= 1 && rows <= shape->B, "bad args");
+  c.fresh = 0;   // the t = 1 slabs are reused by every step of the session
+  const size_t B = shape->B, D = dims->D, V = dims->V, LX2 = c.LX2;
+  Ws& s = c.ws;
+  cudaStream_t st = c.st;
+  const size_t row = sizeof(float) * D;
+  // state in: the step runs as t = 1, so "previous" state lives in the t = 0 outputs
+  SET_CHECK_CUDA(cudaMemcpy2DAsync(s.X2, sizeof(float) * LX2, h1, row, row, rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.c1 + B * D, c1, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.h2 + B * D, h2, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.c2 + B * D, c2, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_PROPAGATE(embed_fwd(tokens, 1, 0, w->embed, dims->V, s.emb_all + B * D, 1, rows, D, 0, 0, kSiteEmb, 0, 0, 1, st));
+  SET_PROPAGATE(project_words(c, 1, 1));
+  SET_PROPAGATE(step_forward(c, feats, 1, rows));
+  GemmProblem p = gemm_problem(rows, V, scores, V);          // fc(h2), editnet.py:653 (eval: dropout is identity)
+  gemm_add_seg(p, s.h2drop + B * D, D, w->fc_w, D, D);
+  p.bias = w->fc_b;
+  SET_PROPAGATE(gemm(kNT, p, st));
+  SET_CHECK_CUDA(cudaMemcpy2DAsync(h1, row, s.X2 + B * LX2, sizeof(float) * LX2, row, rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(c1, s.c1 + 2 * B * D, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(h2, s.h2 + 2 * B * D, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(c2, s.c2 + 2 * B * D, row * rows, cudaMemcpyDeviceToDevice, st));
   return SET_OK;
 }
 

@@ -411,3 +411,100 @@ class DecoderC(EditNetBase):
         pred, call = self._xe(image_features, None, encoded_captions, caption_lengths, encoded_previous_captions,
                               previous_cap_length, use_ss, ss_prob)
         return pred, call.caps, call.decode_lengths, call.sort_ind
+
+
+class StepSession:
+    """Decode steps on explicit state for `k` rows that share nothing but the model (beam search,
+    interactive decoding).  Built by `EditNetBase.step_session`."""
+
+    def __init__(self, mod, image_features, encoded_previous_captions, previous_cap_length, image_mean=None):
+        mod._require_cuda(image_features)
+        mod.flatten_parameters()
+        self.mod = mod
+        self.feats = image_features.contiguous().float()
+        self.image_mean = None if image_mean is None else image_mean.contiguous().float()
+        prev = encoded_previous_captions.contiguous()
+        prev_len = previous_cap_length.contiguous().view(-1)
+        k = self.feats.shape[0]
+        self.dims = mod._dims()
+        self.shape = SetSeqShape(k, self.feats.shape[1], 0, prev.shape[1], int(prev_len.max().item()), 2, 0,
+                                 int(mod.ADAPTIVE))
+        nbytes = _lib.lib().set_editnet_workspace_bytes(C.byref(self.dims), C.byref(self.shape))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.feats.device)
+        check(_lib.lib().set_editnet_step_begin(C.byref(self.dims), C.byref(self.shape), C.byref(mod._struct),
+                                                ptr(self.feats), ptr(self.image_mean), ptr(prev), ptr(prev_len),
+                                                ptr(self.ws), self.ws.numel(), _stream()))
+
+    def init_state(self):
+        k, D = self.shape.B, self.mod.decoder_dim
+        return tuple(torch.zeros(k, D, device=self.feats.device) for _ in range(4))
+
+    def step(self, tokens, state):
+        """tokens (rows,) int64; state = (h1, c1, h2, c2) each (rows, D) -> (scores (rows, V), new state).
+        Equivalent to editnet.py:645-653 (embed .. fc) on the first `rows` rows of the session."""
+        rows = tokens.shape[0]
+        st = [x[:rows].contiguous().clone() for x in state]
+        scores = torch.empty(rows, self.mod.vocab_size, device=self.feats.device)
+        check(_lib.lib().set_editnet_step(C.byref(self.dims), C.byref(self.shape), C.byref(self.mod._struct),
+                                          ptr(self.feats), ptr(tokens.contiguous()), rows, ptr(st[0]), ptr(st[1]),
+                                          ptr(st[2]), ptr(st[3]), ptr(scores), ptr(self.ws), self.ws.numel(), _stream()))
+        return scores, tuple(st)
+
+
+def _step_session(self, image_features, encoded_previous_captions, previous_cap_length, image_mean=None):
+    return StepSession(self, image_features, encoded_previous_captions, previous_cap_length, image_mean)
+
+
+EditNetBase.step_session = _step_session
+
+
+def beam_search(decoder, word_map, image_features, encoded_previous_caption, previous_cap_length, beam_size=3,
+                max_steps=50):
+    """The search loop of evaluate(), editnet.py:608-719, for one image: `image_features` (1,R,F),
+    `encoded_previous_caption` (1,Wp), `previous_cap_length` (1,1).  Each step is ONE library call on the
+    k live beams instead of eight module calls; `top_k_words // vocab_size` replaces the reference's `/`
+    (true division since torch 1.5).  Returns (token list incl. <start>/<end>, score)."""
+    k = beam_size
+    V = decoder.vocab_size
+    dev = image_features.device
+    sess = decoder.step_session(image_features.expand(k, -1, -1), encoded_previous_caption.expand(k, -1),
+                                previous_cap_length.expand(k, -1))                          # :616-621
+    k_prev_words = torch.full((k,), word_map['<start>'], dtype=torch.long, device=dev)     # :623
+    seqs = k_prev_words.unsqueeze(1)                                                        # :626
+    top_k_scores = torch.zeros(k, 1, device=dev)                                            # :629
+    complete_seqs, complete_scores = [], []
+    state = sess.init_state()
+    step = 1
+    while True:
+        scores, state = sess.step(k_prev_words, state)                                      # :645-653
+        scores = torch.log_softmax(scores, dim=1)                                           # :654
+        scores = top_k_scores.expand_as(scores) + scores                                    # :657
+        if step == 1:
+            top_k_scores, top_k_words = scores[0].topk(k, 0, True, True)                    # :660-661
+        else:
+            top_k_scores, top_k_words = scores.view(-1).topk(k, 0, True, True)              # :663
+        prev_word_inds = top_k_words // V                                                   # :666
+        next_word_inds = top_k_words % V                                                    # :667
+        seqs = torch.cat([seqs[prev_word_inds], next_word_inds.unsqueeze(1)], dim=1)        # :670
+        nxt = next_word_inds.tolist()
+        incomplete = [i for i, w in enumerate(nxt) if w != word_map['<end>']]               # :673-674
+        complete = [i for i in range(len(nxt)) if i not in incomplete]
+        if complete:
+            complete_seqs.extend(seqs[complete].tolist())                                   # :678-679
+            complete_scores.extend(top_k_scores[complete].tolist())
+        k -= len(complete)                                                                  # :680
+        if k == 0:
+            break
+        inc = torch.tensor(incomplete, device=dev, dtype=torch.long)
+        seqs = seqs[inc]
+        sel = prev_word_inds[inc]
+        state = tuple(x[sel] for x in state)                                                # :686-691
+        top_k_scores = top_k_scores[inc].unsqueeze(1)
+        k_prev_words = next_word_inds[inc]
+        if step > max_steps:                                                                # :702
+            break
+        step += 1
+    if not complete_scores:
+        return seqs[0].tolist(), float(top_k_scores[0])
+    i = complete_scores.index(max(complete_scores))                                         # :706
+    return complete_seqs[i], complete_scores[i]

@@ -375,3 +375,37 @@ def test_caption_encoder_entry_and_adaptive_six_tuple(small_sd, small_cfg):
     last_logits = torch.stack([pred[i, dl[i] - 1] for i in range(len(dl))]).cpu()
     w, b = small_sd["fc.weight"], small_sd["fc.bias"]
     assert (last_h.cpu() @ w.t() + b - last_logits).abs().max() < 1e-4
+
+
+def test_step_session_and_beam_search_vs_oracle(small_sd, small_cfg):
+    """one decode step on explicit state (the beam-search surface, editnet.py:639-653) and the beam-3
+    search loop built on it, against the oracle's restatement of evaluate()"""
+    _lib, editnet, *_rest, U = _imports()
+    from show_edit_tell_b200.editnet import beam_search
+    c = small_cfg
+    mod, wm = U.build_module(editnet.DecoderC, small_sd, c["V"], c["D"], c["A"], c["Fdim"])
+    mod.eval()
+    b = synth.make_batch(3, c["V"], c["R"], c["Fdim"], c["cap_width"], c["prev_width"], ragged=True, seed=81,
+                         min_len=3, min_prev=2)
+    # (a) two chained steps on 3 different rows vs the oracle cells
+    sess = mod.step_session(b["feats"].cuda(), b["prev"].cuda(), b["prev_len"].cuda())
+    enc = EO.caption_encoder(small_sd, b["prev"], b["prev_len"])
+    st = sess.init_state()
+    rst = tuple(torch.zeros(3, c["D"]) for _ in range(4))
+    toks = torch.tensor([c["V"] - 2, 5, 9])
+    for _ in range(2):
+        scores, st = sess.step(toks.cuda(), st)
+        rst, _ = EO.decoder_step(small_sd, EO.embed(small_sd, toks), rst, enc, b["feats"], b["feats"].mean(1))
+        ref = torch.nn.functional.linear(rst[2], small_sd["fc.weight"], small_sd["fc.bias"])
+        assert (scores.cpu() - ref).abs().max() < TOL
+        for a, r in zip(st, rst):
+            assert (a.cpu() - r).abs().max() < 1e-5
+        toks = ref.argmax(1)
+    # (b) beam search, one image at a time like the reference (batch_size = 1 loader, editnet.py:795-798)
+    for i in range(3):
+        got_seq, got_score = beam_search(mod, wm, b["feats"][i:i + 1].cuda(), b["prev"][i:i + 1].cuda(),
+                                         b["prev_len"][i:i + 1].cuda(), beam_size=3, max_steps=12)
+        ref_seq, ref_score = EO.beam_search(small_sd, wm, b["feats"][i:i + 1], b["prev"][i:i + 1], b["prev_len"][i:i + 1],
+                                            beam_size=3, max_steps=12)
+        assert got_seq == ref_seq, (got_seq, ref_seq)
+        assert abs(got_score - ref_score) < 1e-4
