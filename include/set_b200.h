@@ -131,6 +131,17 @@ SET_API int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape
                            uint64_t seed, float* predictions, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* The same with scheduled sampling (use_ss=True, editnet.py:508-520; train mode only): at steps t >= 1 a
+ * row's input token is, with probability ss_prob, drawn from multinomial(exp(scores of step t-1)) instead of
+ * the ground truth (Philox keyed by `seed`; torch's RNG stream cannot be reproduced).  fed_tokens [B,Wc]
+ * receives the tokens actually fed (pass it as `caps` to set_editnet_xe_backward; the loss still uses the
+ * true captions).  ss_replay [B,Wc] (optional) forces the fed tokens -- used to validate against the oracle. */
+SET_API int set_editnet_xe_forward_ss(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                              const float* feats, const float* image_mean, const int64_t* caps,
+                              const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                              uint64_t seed, float ss_prob, const int64_t* ss_replay, int64_t* fed_tokens,
+                              float* predictions, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward of the above for an upstream gradient d_predictions [B,T,V] (entries at
  * t >= decode_len[i] are ignored, as the reference's slice-assignment does).  Replaces the
  * autograd replay that `loss.backward()` (editnet.py:579) performs through DecoderC.forward.

@@ -167,7 +167,7 @@ def decoder_step(sd, emb, state, enc, feats, image_mean, vis_keep=None, adaptive
 
 # ----------------------------------------------------------------- sequence drivers
 def xe_forward(sd, feats, caps, caplens, prev, prev_len, masks=None, image_mean=None,
-               want_trace=False):
+               want_trace=False, fed_tokens=None, stable_sort=False):
     """DecoderC.forward (teacher forced, use_ss=False), editnet.py:479-548; with
     `image_mean` given, the adaptive variant editnet_adaptive.py:489-562.
 
@@ -177,7 +177,9 @@ def xe_forward(sd, feats, caps, caplens, prev, prev_len, masks=None, image_mean=
     """
     adaptive = image_mean is not None
     B = caps.shape[0]
-    lens, sort_ind = caplens.squeeze(1).sort(dim=0, descending=True)     # :488
+    # :488 -- the reference's sort is unstable: the order inside a group of equal lengths is unspecified
+    # (and differs between CPU and CUDA); stable_sort=True pins it for comparisons at larger batch sizes
+    lens, sort_ind = caplens.squeeze(1).sort(dim=0, descending=True, stable=stable_sort)
     feats, caps = feats[sort_ind], caps[sort_ind]
     prev, prev_len = prev[sort_ind], prev_len[sort_ind]
     decode_lengths = (lens - 1).tolist()                                 # :497
@@ -193,7 +195,10 @@ def xe_forward(sd, feats, caps, caplens, prev, prev_len, masks=None, image_mean=
     trace = {"h1": [], "c1": [], "h2": [], "c2": [], "alpha_c": []}
     for t in range(T):
         b = sum(l > t for l in decode_lengths)                           # :506
-        e = embed(sd, caps[:b, t], None if masks is None else m["emb"][t, :b])
+        # fed_tokens (sorted rows, (B, Wc)): replay of a scheduled-sampling run (:508-520) -- the tokens the
+        # implementation actually fed; None = teacher forcing
+        tok = caps[:b, t] if fed_tokens is None else fed_tokens[:b, t]
+        e = embed(sd, tok, None if masks is None else m["emb"][t, :b])
         enc_b = tuple(x[:b] for x in enc)
         (h1, c1, h2, c2), alpha_c = decoder_step(
             sd, e, (h1[:b], c1[:b], h2[:b], c2[:b]), enc_b, feats[:b], image_mean[:b],

@@ -137,6 +137,9 @@ _SIGS = {
                                    C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "set_editnet_xe_forward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),
                                          _P, _P, _P, C.POINTER(C.c_int), _P, _P, C.c_uint64, _P, _P, C.c_size_t, _P]),
+    "set_editnet_xe_forward_ss": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),
+                                            _P, _P, _P, C.POINTER(C.c_int), _P, _P, C.c_uint64, C.c_float, _P, _P, _P,
+                                            _P, C.c_size_t, _P]),
     "set_editnet_xe_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetEditNetParams),
                                           C.POINTER(SetEditNetParams), _P, _P, C.POINTER(C.c_int), _P, _P,
                                           C.c_uint64, _P, _P, C.c_size_t, _P]),

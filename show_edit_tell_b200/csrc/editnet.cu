@@ -787,43 +787,87 @@ int set_editnet_step(const SetDims* dims, const SetSeqShape* shape, const SetEdi
   return SET_OK;
 }
 
-int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+static int xe_forward_impl(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
                            const float* feats, const float* image_mean, const int64_t* caps,
-                           const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
-                           uint64_t seed, float* predictions, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           const int* decode_len_host, const int64_t* prev, const int64_t* prev_len, uint64_t seed,
+                           float ss_prob, const int64_t* ss_replay, int64_t* fed_tokens, float* predictions,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   Ctx c;
   SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
   SET_REQUIRE(feats && caps && decode_len_host && prev && prev_len, "null input");
   SET_REQUIRE(predictions != nullptr || shape->train, "time-major logits live in the train-mode workspace");
   SET_REQUIRE(shape->Wc > shape->T, "caption width must exceed T");
+  const bool ss = (ss_prob > 0.f) || (ss_replay != nullptr);
+  SET_REQUIRE(!ss || (shape->train && fed_tokens != nullptr), "scheduled sampling needs train mode and fed_tokens");
   std::vector<int> bt;
   SET_PROPAGATE(batch_sizes(*shape, decode_len_host, bt));
   const int B = shape->B, T = shape->T, D = dims->D, V = dims->V;
+  Ws& s = c.ws;
   SET_PROPAGATE(prepare_common(c, feats, image_mean, prev, prev_len));
-  SET_CHECK_CUDA(cudaMemcpyAsync(c.ws.dec_len, decode_len_host, sizeof(int) * B, cudaMemcpyHostToDevice, c.st));
-  SET_PROPAGATE(embed_fwd(caps, shape->Wc, 1, w->embed, V, c.ws.emb_all, T, B, D, shape->train, seed, kSiteEmb, 0, B, 1,
-                          c.st));
-  SET_PROPAGATE(project_words(c, 0, T));
-  SET_PROPAGATE(profile_mark(0, c.st));
-  for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
-  SET_PROPAGATE(profile_mark(1, c.st));
-  // vocabulary projection for all decoded rows at once (editnet.py:545-546), written batch-major
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.dec_len, decode_len_host, sizeof(int) * B, cudaMemcpyHostToDevice, c.st));
+  if (!ss) {
+    SET_PROPAGATE(embed_fwd(caps, shape->Wc, 1, w->embed, V, s.emb_all, T, B, D, shape->train, seed, kSiteEmb, 0, B, 1,
+                            c.st));
+    SET_PROPAGATE(project_words(c, 0, T));
+    SET_PROPAGATE(profile_mark(0, c.st));
+    for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
+    SET_PROPAGATE(profile_mark(1, c.st));
+  } else {
+    // scheduled sampling (editnet.py:508-520): step t's input may be drawn from step t-1's scores, so
+    // the word projections and the vocabulary projection run per step, as in a rollout
+    SET_CHECK_CUDA(cudaMemcpy2DAsync(fed_tokens, sizeof(int64_t) * shape->Wc, caps, sizeof(int64_t) * shape->Wc,
+                                     sizeof(int64_t) * shape->Wc, B, cudaMemcpyDeviceToDevice, c.st));
+    for (int t = 0; t < T; ++t) {
+      const int b = bt[t];
+      ss_choose_kernel<<<b, 256, 0, c.st>>>(t > 0 ? s.logits + (size_t)(t - 1) * B * V : s.logits, V, B, shape->Wc, t,
+                                            ss_prob, seed, caps, ss_replay, s.it + (size_t)t * B, fed_tokens);
+      SET_CHECK_CUDA(cudaGetLastError());
+      set_count_launch(1);
+      SET_PROPAGATE(embed_fwd(s.it + (size_t)t * B, 1, 0, w->embed, V, s.emb_all + (size_t)t * B * D, 1, b, D,
+                              shape->train, seed, kSiteEmb, (long)t * B, 0, 1, c.st));
+      SET_PROPAGATE(project_words(c, t, 1));
+      SET_PROPAGATE(step_forward(c, feats, t, b));
+      GemmProblem p = gemm_problem(b, V, s.logits + (size_t)t * B * V, V);
+      gemm_add_seg(p, s.h2drop + (size_t)t * B * D, D, w->fc_w, D, D);
+      p.bias = w->fc_b; p.c_zeroed = c.fresh;
+      SET_PROPAGATE(gemm(kNT, p, c.st));
+    }
+    if (predictions == nullptr) return SET_OK;   // time-major logits are already in place
+  }
+  // vocabulary projection for all decoded rows at once (editnet.py:545-546)
   if (predictions == nullptr) {
     // fused-trainer form: logits stay time-major [T][B][V] in the workspace (one dense GEMM operand later)
-    GemmProblem p = gemm_problem(T * B, V, c.ws.logits, V);
-    gemm_add_seg(p, c.ws.h2drop, D, w->fc_w, D, D);
-    p.bias = w->fc_b;
+    GemmProblem p = gemm_problem(T * B, V, s.logits, V);
+    gemm_add_seg(p, s.h2drop, D, w->fc_w, D, D);
+    p.bias = w->fc_b; p.c_zeroed = c.fresh;
     SET_PROPAGATE(gemm(kNT, p, c.st));
     return SET_OK;
   }
   SET_CHECK_CUDA(cudaMemsetAsync(predictions, 0, sizeof(float) * (size_t)B * T * V, c.st));
-  GemmProblem p = gemm_problem(T * B, V, predictions, V);
-  gemm_add_seg(p, c.ws.h2drop, D, w->fc_w, D, D);
+  GemmProblem p = gemm_problem(T * B, V, predictions, V);   // written batch-major, undecoded rows stay zero
+  gemm_add_seg(p, s.h2drop, D, w->fc_w, D, D);
   p.bias = w->fc_b;
-  p.c_inner = B; p.c_ld_inner = (long)T * V; p.c_row_len = c.ws.dec_len; p.c_valid_inner = B;
+  p.c_inner = B; p.c_ld_inner = (long)T * V; p.c_row_len = s.dec_len; p.c_valid_inner = B;
   SET_PROPAGATE(gemm(kNT, p, c.st));
   return SET_OK;
+}
+
+int set_editnet_xe_forward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                           const float* feats, const float* image_mean, const int64_t* caps,
+                           const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                           uint64_t seed, float* predictions, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  return xe_forward_impl(dims, shape, w, feats, image_mean, caps, decode_len_host, prev, prev_len, seed, 0.f, nullptr,
+                         nullptr, predictions, workspace, workspace_bytes, stream);
+}
+
+int set_editnet_xe_forward_ss(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,
+                              const float* feats, const float* image_mean, const int64_t* caps,
+                              const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
+                              uint64_t seed, float ss_prob, const int64_t* ss_replay, int64_t* fed_tokens,
+                              float* predictions, void* workspace, size_t workspace_bytes, void* stream) {
+  return xe_forward_impl(dims, shape, w, feats, image_mean, caps, decode_len_host, prev, prev_len, seed, ss_prob,
+                         ss_replay, fed_tokens, predictions, workspace, workspace_bytes, stream);
 }
 
 int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const SetEditNetParams* w,

@@ -135,6 +135,63 @@ __global__ void __launch_bounds__(256) sample_step_kernel(const float* __restric
   }
 }
 
+// Scheduled sampling (editnet.py:508-520): the token fed at step t >= 1 is, with probability ss_prob,
+// a draw from multinomial(exp(logits of step t-1)) (the reference exponentiates raw logits, :517;
+// multinomial normalises, so this is softmax sampling), else the ground-truth token.  `replay`
+// (batch-major [B][Wc]) overrides the choice (tests).  One block per row; writes the time-major feed
+// `it_t` and the batch-major record `fed` (consumed by the backward pass as "the captions").
+__global__ void __launch_bounds__(256) ss_choose_kernel(const float* __restrict__ logits_prev, int V, int B, int Wc,
+                                                        int t, float ss_prob, uint64_t seed,
+                                                        const int64_t* __restrict__ caps,
+                                                        const int64_t* __restrict__ replay,
+                                                        int64_t* __restrict__ it_t, int64_t* __restrict__ fed) {
+  __shared__ float red[40];
+  __shared__ float csum[256];
+  __shared__ float wm[8];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const int64_t gt = caps[(long)i * Wc + t];
+  int64_t tok = gt;
+  bool sample = false;
+  if (replay) tok = replay[(long)i * Wc + t];
+  else if (t >= 1 && ss_prob > 0.f) sample = philox_uniform(seed, kSiteSample, (uint64_t)(2 * t) * B + i) < ss_prob;
+  if (sample) {   // block-uniform
+    const float* x = logits_prev + (long)i * V;
+    float m = -INFINITY;
+    for (int v = tid; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+    m = warp_max(m);
+    if ((tid & 31) == 0) wm[tid >> 5] = m;
+    __syncthreads();
+    m = wm[0];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmaxf(m, wm[k]);
+    const int chunk = (V + blockDim.x - 1) / blockDim.x;
+    const int v0 = tid * chunk, v1 = min(V, v0 + chunk);
+    float loc = 0.f;
+    for (int v = v0; v < v1; ++v) loc += expf(x[v] - m);
+    csum[tid] = loc;
+    const float sum = block_sum(loc, red);
+    if (tid == 0) {
+      const float u = philox_uniform(seed, kSiteSample, (uint64_t)(2 * t + 1) * B + i) * sum;
+      float run = 0.f;
+      int sel_t = blockDim.x - 1;
+      for (int k = 0; k < (int)blockDim.x; ++k) {
+        if (run + csum[k] > u) { sel_t = k; break; }
+        run += csum[k];
+      }
+      const int a0 = sel_t * chunk, a1 = min(V, a0 + chunk);
+      int pick = max(a1 - 1, 0);
+      for (int v = a0; v < a1; ++v) {
+        run += expf(x[v] - m);
+        if (run > u) { pick = v; break; }
+      }
+      tok = pick;
+    }
+  }
+  if (tid == 0) {
+    it_t[i] = tok;
+    fed[(long)i * Wc + t] = tok;
+  }
+}
+
 // d logits[t][i][v] = d_slp[i][t] * (1[v == tok] - softmax_v)   (in place over the saved logits)
 __global__ void rollout_dlogits_kernel(float* __restrict__ logits, int V, int B, int T,
                                        const float* __restrict__ d_slp, const float* __restrict__ lse,

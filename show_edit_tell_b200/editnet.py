@@ -287,6 +287,16 @@ class EditNetBase(nn.Module):
     def _xe_forward_raw(self, call):
         s = call.shape
         pred = torch.empty(s.B, s.T, self.vocab_size, device=call.feats.device, dtype=torch.float32)
+        ss_prob = getattr(call, "ss_prob", 0.0)
+        replay = getattr(call, "ss_replay", None)
+        if ss_prob > 0.0 or replay is not None:
+            call.fed = torch.empty_like(call.caps)
+            check(_lib.lib().set_editnet_xe_forward_ss(
+                C.byref(call.dims), C.byref(s), C.byref(self._struct), ptr(call.feats), ptr(call.image_mean),
+                ptr(call.caps), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, ss_prob, ptr(replay),
+                ptr(call.fed), ptr(pred), ptr(call.ws), call.ws.numel(), _stream()))
+            return pred
+        call.fed = call.caps
         check(_lib.lib().set_editnet_xe_forward(
             C.byref(call.dims), C.byref(s), C.byref(self._struct), ptr(call.feats), ptr(call.image_mean),
             ptr(call.caps), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, ptr(pred), ptr(call.ws),
@@ -297,17 +307,18 @@ class EditNetBase(nn.Module):
         g = self._struct_for(flat_grad)
         check(_lib.lib().set_editnet_xe_backward(
             C.byref(call.dims), C.byref(call.shape), C.byref(self._struct), C.byref(g), ptr(call.feats),
-            ptr(call.caps), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, ptr(dpred), ptr(call.ws),
+            ptr(call.fed), call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, ptr(dpred), ptr(call.ws),
             call.ws.numel(), _stream()))
 
     def _xe(self, image_features, image_mean, encoded_captions, caption_lengths, encoded_previous_captions,
             previous_cap_length, use_ss, ss_prob):
-        if use_ss and ss_prob > 0.0:
-            raise NotImplementedError(
-                "scheduled sampling (editnet.py:508-520) is not built yet: call with ss_prob = 0 "
-                "(the reference's own setting for epochs 0-4, editnet.py:812-816)")
         call = self._prepare_xe(image_features, image_mean, encoded_captions, caption_lengths,
                                 encoded_previous_captions, previous_cap_length)
+        if use_ss and ss_prob > 0.0:                       # scheduled sampling, editnet.py:508-520
+            if not self.training:
+                raise RuntimeError("scheduled sampling is a training-time feature (train mode required)")
+            call.ss_prob = float(ss_prob)
+        call.ss_replay = getattr(self, "_ss_replay", None)  # tests: force the fed tokens
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             pred = _XEFunction.apply(self, call, *self._ordered_params())
         else:

@@ -409,3 +409,36 @@ def test_step_session_and_beam_search_vs_oracle(small_sd, small_cfg):
                                             beam_size=3, max_steps=12)
         assert got_seq == ref_seq, (got_seq, ref_seq)
         assert abs(got_score - ref_score) < 1e-4
+
+
+def test_scheduled_sampling_replay_and_statistics(small_sd, small_cfg):
+    """use_ss=True (editnet.py:508-520): torch's RNG cannot be matched, so (a) the tokens the kernels fed are
+    replayed through the oracle (logits + gradients must agree), (b) the substitution rate is checked."""
+    _lib, editnet, *_rest, U = _imports()
+    c = small_cfg
+    B = 48
+    batch = synth.make_batch(B, c["V"], c["R"], c["Fdim"], c["cap_width"], c["prev_width"], ragged=True, seed=91,
+                             min_len=3, min_prev=2)
+    mod, _ = U.build_module(editnet.DecoderC, small_sd, c["V"], c["D"], c["A"], c["Fdim"])
+    mod.train()
+    torch.manual_seed(3)
+    ss_prob = 0.5
+    pred, caps_sorted, dl, sort_ind = mod(*_cuda(batch, XE_KEYS), True, ss_prob)
+    fed = mod._last_call.fed.cpu()
+    caps_s = caps_sorted.cpu()
+    T = max(dl)
+    assert torch.equal(fed[:, 0], caps_s[:, 0])                       # t = 0 is never sampled (:508)
+    n_pos = sum(max(0, l - 1) for l in dl)                            # decoded positions with t >= 1
+    changed = sum(int(fed[i, t] != caps_s[i, t]) for i in range(B) for t in range(1, dl[i]))
+    rate = changed / n_pos
+    print("scheduled sampling: %d/%d fed tokens differ from the ground truth (ss_prob %.2f)" % (changed, n_pos, ss_prob))
+    assert abs(rate - ss_prob * (1 - 1.0 / c["V"])) < 4 * (0.25 / n_pos) ** 0.5
+    masks = U.keep_masks(mod.last_seed, B, T, c["prev_width"], c["D"], c["R"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in small_sd.items()}
+    # undo the sort for the oracle's input, replay the fed tokens (already in sorted order)
+    rp, rc, rdl, _ = EO.xe_forward(sd, batch["feats"], batch["caps"], batch["caplens"], batch["prev"], batch["prev_len"],
+                                   masks, fed_tokens=fed, stable_sort=True)
+    assert rdl == dl
+    assert (pred.detach().cpu() - rp.detach()).abs().max() < TOL
+    EO.xe_loss(pred, caps_sorted, dl).backward()
+    assert not U.compare_grads(U.grads_by_key(mod), U.oracle_grads(sd, EO.xe_loss(rp, rc, rdl)), GTOL, "scheduled sampling")
