@@ -192,6 +192,7 @@ class EditNetBase(nn.Module):
         self._flat = None
         self._offsets = None
         self._struct = None
+        self._last_call = None
         self.last_seed = None
 
     def __getstate__(self):

@@ -80,6 +80,7 @@ class XETrainer:
                                        self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
                                        ptr(count_dev), ptr(st["scratch"]), _stream()))
         self.last_call = call
+        dec._last_call = call
         loss = st["loss"][0]
         if self.distributed:
             loss = loss / st["loss"][1]
@@ -90,3 +91,61 @@ class XETrainer:
 
     def flat_grad(self):
         return self._state["grad"][:self._state["n"]]
+
+
+class SCSTTrainer:
+    """Self-critical step of editnet_rl.py:649-679 without autograd: greedy rollout (eval, no grad) ->
+    sampled rollout (train mode, dropout on) -> reward -> RewardCriterion -> reverse pass -> [all-reduce]
+    -> clip 0.25 + Adam.  `reward_fn(sample_seq, greedy_seq) -> (B, max_len) float tensor` stands where
+    the reference calls CIDEr-D on the host (`get_self_critical_reward`, editnet_rl.py:611-646): that
+    scorer (pyciderevalcap) is out of scope, so the caller supplies the rewards."""
+
+    def __init__(self, decoder, lr=5e-5, max_norm=0.25, betas=(0.9, 0.999), eps=1e-8, process_group=None,
+                 distributed=None, max_len=18):
+        self.decoder = decoder
+        self.lr, self.max_norm, self.betas, self.eps, self.max_len = lr, max_norm, betas, eps, max_len
+        self.distributed = dist.is_initialized() if distributed is None else distributed
+        self.group = process_group
+        self.step_count = 0
+        self._state = None
+
+    _ensure_state = XETrainer._ensure_state
+
+    def step(self, word_map, image_features, encoded_previous_captions, previous_cap_length, reward_fn,
+             image_mean=None, seed=None):
+        dec = self.decoder
+        flat, st = self._ensure_state()
+        L = _lib.lib()
+        start, end = word_map['<start>'], word_map['<end>']
+        dec.eval()      # greedy baseline, editnet_rl.py:665-668
+        g = dec._prepare_rollout(encoded_previous_captions, previous_cap_length, image_features, image_mean, 0,
+                                 self.max_len, start, end, keep=False)
+        greedy_seq, _ = dec._rollout_raw(g)
+        dec.train()     # sampled rollout with dropout, editnet_rl.py:669-671
+        call = dec._prepare_rollout(encoded_previous_captions, previous_cap_length, image_features, image_mean, 1,
+                                    self.max_len, start, end, seed=seed, keep=True)
+        seq, slp = dec._rollout_raw(call)
+        reward = reward_fn(seq, greedy_seq).to(slp.device, torch.float32).contiguous()
+        dlp = torch.empty_like(slp)
+        check(L.set_reward_criterion(seq.shape[0], seq.shape[1], ptr(slp), ptr(seq), ptr(reward), ptr(st["loss"]),
+                                     ptr(dlp), _stream()))
+        grad = st["grad"]
+        grad.zero_()
+        if self.distributed:
+            # ranks contribute sums over their rows: undo the local 1/sum(mask), carry the mask count along
+            mask_sum = torch.cat([torch.ones_like(seq[:, :1]), (seq[:, :-1] > 0).long()], 1).sum().float()
+            dlp.mul_(mask_sum)
+        dec._rollout_backward_raw(call, dlp, grad[:st["n"]])
+        count_dev = None
+        if self.distributed:
+            count_dev = allreduce_sums(grad, st["n"], mask_sum, self.group)
+        self.step_count += 1
+        check(L.set_clip_adam(ptr(flat), ptr(grad), ptr(st["m"]), ptr(st["v"]), st["n"], self.step_count, self.lr,
+                              self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0, ptr(count_dev),
+                              ptr(st["scratch"]), _stream()))
+        self.last_call, self.last_seq, self.last_greedy = call, seq, greedy_seq
+        dec._last_call = call
+        return st["loss"][0]
+
+    grad_norm = XETrainer.grad_norm
+    flat_grad = XETrainer.flat_grad

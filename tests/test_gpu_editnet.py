@@ -442,3 +442,36 @@ def test_scheduled_sampling_replay_and_statistics(small_sd, small_cfg):
     assert (pred.detach().cpu() - rp.detach()).abs().max() < TOL
     EO.xe_loss(pred, caps_sorted, dl).backward()
     assert not U.compare_grads(U.grads_by_key(mod), U.oracle_grads(sd, EO.xe_loss(rp, rc, rdl)), GTOL, "scheduled sampling")
+
+
+def test_scst_trainer_step_vs_oracle(small_sd, small_cfg):
+    """one self-critical step (editnet_rl.py:649-679): greedy + sampled rollouts, RewardCriterion, reverse
+    pass; the sampled tokens are replayed through the oracle to check loss and gradients"""
+    _lib, editnet, editnet_rl, editnet_adaptive, trainmod, U = _imports()
+    c = small_cfg
+    b = synth.make_batch(c["B"], c["V"], c["R"], c["Fdim"], c["cap_width"], c["prev_width"], ragged=True, seed=95,
+                         min_len=3, min_prev=2)
+    mod, wm = U.build_module(editnet_rl.DecoderC, small_sd, c["V"], c["D"], c["A"], c["Fdim"])
+    tr = trainmod.SCSTTrainer(mod, distributed=False)
+    g0 = torch.Generator().manual_seed(8)
+    reward_rows = torch.randn(c["B"], 1, generator=g0)
+
+    def reward_fn(sample_seq, greedy_seq):
+        assert sample_seq.shape == greedy_seq.shape == (c["B"], 18)
+        return reward_rows.repeat(1, 18)
+
+    loss = tr.step(wm, b["feats"].cuda(), b["prev"].cuda(), b["prev_len"].cuda(), reward_fn, seed=123)
+    V = c["V"]
+    with torch.no_grad():     # greedy baseline equals the oracle's greedy rollout
+        gseq, _ = EO.rollout(small_sd, b["prev"], b["prev_len"], b["feats"], V - 2, V - 1, "greedy")
+    assert torch.equal(tr.last_greedy.cpu(), gseq)
+    raw = mod.workspace_tensor("tok_raw", torch.int64).view(18, c["B"]).t().cpu()     # sampled tokens before rewrite
+    forced = torch.where(raw < 0, torch.zeros_like(raw), raw)
+    masks = U.keep_masks(123, c["B"], 18, c["prev_width"], c["D"], c["R"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in small_sd.items()}
+    rseq, rslp = EO.rollout(sd, b["prev"], b["prev_len"], b["feats"], V - 2, V - 1, "forced", masks=masks, forced=forced)
+    assert torch.equal(tr.last_seq.cpu(), rseq)
+    rloss = EO.reward_criterion(rslp, rseq, reward_rows.repeat(1, 18))
+    assert abs(float(loss) - float(rloss.detach())) < 1e-5
+    mine = dict(zip([k for _, k in _lib.EDITNET_FIELDS], mod._views(tr.flat_grad())))
+    assert not U.compare_grads(mine, U.oracle_grads(sd, rloss), GTOL, "scst")
