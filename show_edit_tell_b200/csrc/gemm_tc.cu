@@ -33,7 +33,8 @@ namespace {
 
 constexpr int kBlockK = 32;        // fp32 per smem row: 128 B = one swizzle span
 constexpr int kTileP = 128;        // UMMA M
-constexpr int kThreadsTc = 192;
+constexpr int kConvWarps = 8;       // hi/lo converters (two per TMEM lane quarter), also the epilogue warps
+constexpr int kThreadsTc = 64 + 32 * kConvWarps;
 
 struct TcParams {
   CUtensorMap mapP[4];
@@ -49,6 +50,7 @@ struct TcParams {
   const float* bias; const float* bias2;
   const float* add; long ldadd; int add_mod;
   int beta, act;
+  int a_tmem;                      // 1: the P operand is fed to the MMA from tensor memory (hi/lo written by tcgen05.st)
   unsigned idesc_xor;              // debugging aid (SET_TC_IDESC_XOR)
   unsigned long long* trace;       // debugging aid: per-phase %globaltimer stamps of CTA 0 (SET_TC_TRACE)
 };
@@ -107,6 +109,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory: [128 lanes] x [8 columns of tf32] at `tmem_a`
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+constexpr uint32_t kTmemABase = 128;   // columns [0,128): accumulator; [128 + 64*stage, +64): P_hi | P_lo of a stage
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -174,15 +194,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 4);
+      mbar_init(conv_bar(s), kConvWarps);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)QN)
-                 : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(prm.a_tmem ? 512u : (uint32_t)QN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -244,9 +264,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
           const uint64_t a_lo = umma_desc(p_lo + k * p_step, p_lbo, 1024u);
           const uint64_t b_hi = umma_desc(q_hi + k * q_step, q_lbo, 1024u);
           const uint64_t b_lo = umma_desc(q_lo + k * q_step, q_lbo, 1024u);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc_final, (i > 0 || k > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, a_hi, b_lo, idesc_final, 1u);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc_final, 1u);
+          if (prm.a_tmem) {
+            const uint32_t ta_hi = tmem_base + kTmemABase + (uint32_t)s * 64u + (uint32_t)k * 8u;
+            umma_tf32_ts(tmem_base, ta_hi + 32u, b_hi, idesc_final, (i > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts(tmem_base, ta_hi, b_lo, idesc_final, 1u);
+            umma_tf32_ts(tmem_base, ta_hi, b_hi, idesc_final, 1u);
+          } else {
+            umma_tf32(tmem_base, a_lo, b_hi, idesc_final, (i > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, a_hi, b_lo, idesc_final, 1u);
+            umma_tf32(tmem_base, a_hi, b_hi, idesc_final, 1u);
+          }
         }
         umma_commit(empty_bar(s));   // smem slot reusable once these MMAs retire
       }
@@ -254,7 +281,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
     }
   } else {
     // ============================== converters, then epilogue ==============================
-    const int ct = threadIdx.x - 64;   // 0..127
+    const int ct = threadIdx.x - 64;   // 0 .. 32*kConvWarps-1
+    constexpr int kCT = 32 * kConvWarps;
+    const int khalf = (warp - 2) >> 2;  // which 16-column half of the K-block this warp converts (A-from-TMEM)
     for (int i = 0; i < nkb; ++i) {
       const int s = i % S;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
@@ -269,23 +298,48 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
         hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
         lo = x - hi;
       };
+      if (prm.a_tmem) {
+        // P (the 128-row operand) goes to tensor memory: this thread owns tile row `prow` = its TMEM lane,
+        // reads the row's 32 fp32 out of the 128B-swizzled tile (16-byte chunk c of row r sits at chunk
+        // c ^ (r & 7)) and stores hi | lo as 2 x 32 columns.  No shared-memory write-back, and the MMA
+        // no longer re-reads P from shared memory -- the two largest smem streams of the SS form.
+        const int prow = (warp & 3) * 32 + lane;
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < Cfg::kPBytes / 16 / 128; ++j) {
-        const float4 v = p_hi[ct + 128 * j];
-        float4 h, l;
-        split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
-        p_hi[ct + 128 * j] = h;
-        p_lo[ct + 128 * j] = l;
+        for (int cc = 0; cc < 4; ++cc) {
+          const int cch = khalf * 4 + cc;
+          const float4 v = p_hi[prow * 8 + (cch ^ (prow & 7))];
+          float h, l;
+          split(v.x, h, l); hi[cc * 4 + 0] = __float_as_uint(h); lo[cc * 4 + 0] = __float_as_uint(l);
+          split(v.y, h, l); hi[cc * 4 + 1] = __float_as_uint(h); lo[cc * 4 + 1] = __float_as_uint(l);
+          split(v.z, h, l); hi[cc * 4 + 2] = __float_as_uint(h); lo[cc * 4 + 2] = __float_as_uint(l);
+          split(v.w, h, l); hi[cc * 4 + 3] = __float_as_uint(h); lo[cc * 4 + 3] = __float_as_uint(l);
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemABase + (uint32_t)s * 64u +
+                            (uint32_t)khalf * 16u;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < Cfg::kPBytes / 16 / kCT; ++j) {
+          const float4 v = p_hi[ct + kCT * j];
+          float4 h, l;
+          split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
+          p_hi[ct + kCT * j] = h;
+          p_lo[ct + kCT * j] = l;
+        }
       }
 #pragma unroll
-      for (int j = 0; j < Cfg::kQBytes / 16 / 128; ++j) {
-        const float4 v = q_hi[ct + 128 * j];
+      for (int j = 0; j < Cfg::kQBytes / 16 / kCT; ++j) {
+        const float4 v = q_hi[ct + kCT * j];
         float4 h, l;
         split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
-        q_hi[ct + 128 * j] = h;
-        q_lo[ct + 128 * j] = l;
+        q_hi[ct + kCT * j] = h;
+        q_lo[ct + kCT * j] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(conv_bar(s));
       if (ct == 0 && i == 0) TC_STAMP(3);
@@ -302,12 +356,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
     // along the contiguous global direction: 128-bit global loads/stores/reductions, several rows in
     // flight per thread, no serial latency chain.
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const bool stager = (warp - 2) < 4;         // one warp per quarter moves TMEM -> smem
     constexpr int EPW_N = QN + 4;              // staged row pitch, non-swap: [128 p][QN q]
     constexpr int EPW_S = kTileP + 4;          // staged row pitch, swap:     [QN q][128 p]
     float* ep = reinterpret_cast<float*>(gen_base);
     const int prow = quarter * 32 + lane;      // tile row held by this thread
 #pragma unroll 1
-    for (int cb = 0; cb < QN / 32; ++cb) {
+    for (int cb = 0; stager && cb < QN / 32; ++cb) {
       uint32_t r[32];
       if (nkb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), r);
@@ -326,7 +381,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
                           __uint_as_float(r[j + 3]));
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");   // converter/epilogue warps only
     if (ct == 0) TC_STAMP(6);
     const bool lead = (ks == 0);               // split 0 carries bias / addend
     const bool atomic = prm.split_k > 1;
@@ -337,7 +392,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
     const int vec_per_row = width / 4;
     const int total_vec = (prm.swap ? QN : kTileP) * vec_per_row;
 #pragma unroll 4
-    for (int e = ct; e < total_vec; e += 128) {
+    for (int e = ct; e < total_vec; e += kCT) {
       const int o = e / vec_per_row, i4 = (e % vec_per_row) * 4;
       const int m = m_base + o, n = n_base + i4;
       if (m >= m_lim || n >= n_lim) continue;
@@ -385,7 +440,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   if (threadIdx.x == 64) TC_STAMP(8);
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)QN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(prm.a_tmem ? 512u : (uint32_t)QN) : "memory");
   }
 }
 
@@ -482,6 +538,10 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   prm.beta = g.beta; prm.act = g.act;
   { const char* e = getenv("SET_TC_IDESC_XOR"); prm.idesc_xor = e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }
   prm.trace = g_tc_trace;
+  {
+    static const int atmem = getenv("SET_TC_ATMEM") ? atoi(getenv("SET_TC_ATMEM")) : 1;
+    prm.a_tmem = (atmem && !prm.p_mn) ? 1 : 0;
+  }
   return true;
 }
 
