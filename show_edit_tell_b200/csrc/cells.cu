@@ -425,12 +425,23 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
     const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
     for (int j = wid; j < n; j += nw) {
       float s = 0.f;
-#pragma unroll 8
-      for (int d = lane; d < a.D; d += 32) s += dc[d] * ph[(long)j * a.D + d];
+      {
+        const float4* x4 = reinterpret_cast<const float4*>(dc);
+        const float4* y4 = reinterpret_cast<const float4*>(ph + (long)j * a.D);
+#pragma unroll 4
+        for (int d = lane; d < a.D / 4; d += 32) {
+          const float4 x = x4[d], y = __ldg(y4 + d);
+          s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        }
+      }
       if (j == js) {
-        const float* pm = a.prev_m + ((long)i * a.P + j) * a.D;
-        const float* dsl = a.dsel + (long)i * a.D;
-        for (int d = lane; d < a.D; d += 32) s += dsl[d] * pm[d];
+        const float4* y4 = reinterpret_cast<const float4*>(a.prev_m + ((long)i * a.P + j) * a.D);
+        const float4* x4 = reinterpret_cast<const float4*>(a.dsel + (long)i * a.D);
+#pragma unroll 4
+        for (int d = lane; d < a.D / 4; d += 32) {
+          const float4 x = x4[d], y = __ldg(y4 + d);
+          s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        }
       }
       s = warp_sum(s);
       if (lane == 0) dal[j] = s;
@@ -441,8 +452,13 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
     for (int r = wid; r < n; r += nw) {
       float s = 0.f;
       if (r < nvalid) {
-#pragma unroll 8
-        for (int f = lane; f < a.F; f += 32) s += di[f] * ft[(long)r * a.F + f];
+        const float4* x4 = reinterpret_cast<const float4*>(di);
+        const float4* y4 = reinterpret_cast<const float4*>(ft + (long)r * a.F);
+#pragma unroll 4
+        for (int f = lane; f < a.F / 4; f += 32) {
+          const float4 x = x4[f], y = __ldg(y4 + f);
+          s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        }
       }
       s = warp_sum(s);
       if (lane == 0) dal[r] = s;

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "gemm.cuh"
 
@@ -152,14 +153,15 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+template <int G>
 struct TcGroup {
   int n;
   int cta_start[9];        // first CTA of each problem (tiles * split_k each)
-  TcParams p[8];
+  TcParams p[G];
 };
 
-template <int QN>
-__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_constant__ TcGroup grp) {
+template <int QN, int G>
+__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_constant__ TcGroup<G> grp) {
   using Cfg = TcCfg<QN>;
   int pi = 0;
   while (pi + 1 < grp.n && (int)blockIdx.x >= grp.cta_start[pi + 1]) ++pi;
@@ -461,8 +463,15 @@ void tc_init() {
     return;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes) != cudaSuccess) {
+  bool ok = true;
+  auto set_attr = [&](auto kern, int bytes) {
+    ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+  };
+  set_attr(gemm_tc_kernel<64, 1>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 1>, TcCfg<128>::kSmemBytes);
+  set_attr(gemm_tc_kernel<64, 2>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 2>, TcCfg<128>::kSmemBytes);
+  set_attr(gemm_tc_kernel<64, 5>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 5>, TcCfg<128>::kSmemBytes);
+  set_attr(gemm_tc_kernel<64, 8>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8>, TcCfg<128>::kSmemBytes);
+  if (!ok) {
     cudaGetLastError();
     g_tc_failed = true;
     return;
@@ -560,7 +569,7 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     const int small = g.M < g.N ? g.M : g.N;
     if (small > 64) QN = 128;
   }
-  static TcGroup grp;     // host staging (launch copies it); calls are serialised by the caller's stream use
+  static TcGroup<8> grp;  // host staging (launch copies it); calls are serialised by the caller's stream use
   grp.n = 0;
   long tiles_total = 0;
   int idx[8];
@@ -598,8 +607,19 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     taken[idx[k]] = true;
   }
   grp.cta_start[grp.n] = cta;
-  if (QN == 64) gemm_tc_kernel<64><<<cta, kThreadsTc, TcCfg<64>::kSmemBytes, stream>>>(grp);
-  else gemm_tc_kernel<128><<<cta, kThreadsTc, TcCfg<128>::kSmemBytes, stream>>>(grp);
+  auto launch = [&](auto tag) {
+    constexpr int G = decltype(tag)::value;
+    TcGroup<G> small;
+    small.n = grp.n;
+    memcpy(small.cta_start, grp.cta_start, sizeof(small.cta_start));
+    memcpy(small.p, grp.p, sizeof(TcParams) * grp.n);
+    if (QN == 64) gemm_tc_kernel<64, G><<<cta, kThreadsTc, TcCfg<64>::kSmemBytes, stream>>>(small);
+    else gemm_tc_kernel<128, G><<<cta, kThreadsTc, TcCfg<128>::kSmemBytes, stream>>>(small);
+  };
+  if (grp.n == 1) launch(std::integral_constant<int, 1>{});
+  else if (grp.n == 2) launch(std::integral_constant<int, 2>{});
+  else if (grp.n <= 5) launch(std::integral_constant<int, 5>{});
+  else launch(std::integral_constant<int, 8>{});
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
   return SET_OK;
