@@ -2,6 +2,8 @@
 // of each launcher and the reference lines it reproduces.
 #include "cells.cuh"
 
+#include <mutex>
+
 namespace set {
 
 namespace {
@@ -661,7 +663,30 @@ __global__ void keep_mask_kernel(float* __restrict__ out, long n, uint64_t seed,
     out[y] = drop_keep(seed, site, (uint64_t)(base + y)) ? 1.f : 0.f;
 }
 
+// The tensor-core GEMM needs the maximum shared-memory carveout (197 KB of dynamic smem).  If the small
+// kernels that run between two GEMM launches ask for the default split, every SM is drained and
+// re-partitioned at each boundary (~10 us per launch on B200).  All kernels of the path therefore
+// declare the same preference once.
+static std::once_flag g_carveout_once;
+template <typename K>
+static void prefer_smem(K kern) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static void init_carveout() {
+  prefer_smem(embed_fwd_kernel); prefer_smem(embed_bwd_kernel); prefer_smem(region_mean_kernel);
+  prefer_smem(region_count_kernel); prefer_smem(zero_pad_regions_kernel); prefer_smem(vis_dropout_fwd_kernel);
+  prefer_smem(vis_dropout_bwd_kernel); prefer_smem(relu_bwd_kernel); prefer_smem(tanh_bwd_kernel);
+  prefer_smem(lstm_fwd_kernel); prefer_smem(lstm_bwd_kernel); prefer_smem(enc_lstm_bwd_kernel);
+  prefer_smem(bilstm_fwd_kernel); prefer_smem(bilstm_bwd_kernel); prefer_smem(enc_mask_kernel);
+  prefer_smem(attention_fwd_kernel); prefer_smem(attention_bwd_kernel); prefer_smem(ctx_gate_fwd_kernel);
+  prefer_smem(ctx_gate_bwd_kernel); prefer_smem(copy1_fwd_kernel); prefer_smem(copy2_fwd_kernel);
+  prefer_smem(copy2_bwd_kernel); prefer_smem(copy1_bwd_kernel); prefer_smem(dropout_fwd_kernel);
+  prefer_smem(transpose_kernel); prefer_smem(sum_time_kernel); prefer_smem(keep_mask_kernel);
+  cudaGetLastError();
+}
+
 #define LAUNCH_OK()                         \
+  std::call_once(g_carveout_once, init_carveout); \
   SET_CHECK_CUDA(cudaGetLastError());       \
   set_count_launch(1);                      \
   return SET_OK

@@ -181,6 +181,12 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmG
 
 template <int MODE, int BN>
 int launch(const GemmGroup& g, int total_tiles, cudaStream_t stream) {
+  static const bool once = [] {   // same carveout preference as the tensor-core kernel (see cells.cu)
+    cudaFuncSetAttribute(gemm_kernel<MODE, BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)once;
   gemm_kernel<MODE, BN><<<total_tiles, 256, 0, stream>>>(g);
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
@@ -264,6 +270,11 @@ int colsum(const float* X, long ld, int M, int N, float* out, int beta, cudaStre
   if (N <= 0) return SET_OK;
   if (!beta) SET_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
   if (M <= 0) return SET_OK;
+  static const bool once = [] {
+    cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)once;
   dim3 block(32, 8);
   int gy = (M + 255) / 256;
   if (gy > 64) gy = 64;

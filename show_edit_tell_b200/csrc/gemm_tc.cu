@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 64) TC_STAMP(0);
+  if (prm.trace && threadIdx.x == 0 && blockIdx.x < 1000) prm.trace[16 + 2 * blockIdx.x] = gtimer();   // per-CTA start
 
   // tile / split decode
   int bid = blockIdx.x - grp.cta_start[pi];
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 64) TC_STAMP(8);
+  if (prm.trace && threadIdx.x == 0 && blockIdx.x < 1000) prm.trace[17 + 2 * blockIdx.x] = gtimer();   // per-CTA end
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(prm.a_tmem ? 512u : (uint32_t)QN) : "memory");
