@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libset_b200.so")
+LIB_PATH = os.environ.get("SET_LIB_PATH") or os.path.join(_HERE, "libset_b200.so")   # override: kernel experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 
@@ -170,6 +170,7 @@ _SIGS = {
     "set_dropout_keep_mask": (C.c_int, [_P, C.c_size_t, C.c_uint64, C.c_int, C.c_size_t, _P]),
     "set_gemm_backend": (C.c_int, [C.c_int]),
     "set_gemm_trace": (C.c_int, [_P]),
+    "set_gemm_trace_seq": (C.c_int, [_P, C.c_long, C.c_int]),
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_long, _P, C.c_long, _P, _P, C.c_long,
                            C.c_int, C.c_int, _P]),

@@ -162,6 +162,8 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, long ld_pre, cons
                                 float* __restrict__ c_out, float* __restrict__ h_out, long ld_h, int rows, int D,
                                 const int64_t* __restrict__ len, int t, float* __restrict__ seq_h,
                                 float* __restrict__ seq_m, long seq_ld) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -203,6 +205,8 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __
                                 const float* __restrict__ c_cur, const float* __restrict__ dh, long ld_dh,
                                 const float* __restrict__ dh_b, float* __restrict__ dc_carry,
                                 float* __restrict__ dgates, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -223,6 +227,8 @@ __global__ void enc_lstm_bwd_kernel(const float* __restrict__ gates, const float
                                     const float* __restrict__ dseq_m, long seq_ld,
                                     const float* __restrict__ dh_last, const int64_t* __restrict__ len, int t,
                                     float* __restrict__ dgates, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -319,6 +325,8 @@ __global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restr
 // ------------------------------------------------------------------------ attention
 // dynamic smem: a2[A] | wv[A] | sc[max(P,R)] | red[40]
 __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnFwdArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int A = a.A;
   float* a2 = sm;
@@ -400,6 +408,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnF
 
 // dynamic smem: a2[A] | wv[A] | al[n] | dal[n] | ds[n] | red[40]
 __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnBwdArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int A = a.A;
   const bool cap = (blockIdx.y == 0);
@@ -526,6 +536,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
 __global__ void ctx_gate_fwd_kernel(const float* __restrict__ s4, long ld_s4, const float* __restrict__ th,
                                     long ld_th, float* __restrict__ zst, float* __restrict__ att_cap,
                                     long ld_cap, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -541,6 +553,8 @@ __global__ void ctx_gate_fwd_kernel(const float* __restrict__ s4, long ld_s4, co
 __global__ void ctx_gate_bwd_kernel(const float* __restrict__ zst, const float* __restrict__ datt_cap,
                                     long ld_dcap, float* __restrict__ dz_out, float* __restrict__ dtc_out,
                                     long ld_ds2, float* __restrict__ dsc, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -557,6 +571,8 @@ __global__ void ctx_gate_bwd_kernel(const float* __restrict__ zst, const float* 
 // ------------------------------------------------------------------------ copy-LSTM
 __global__ void copy1_fwd_kernel(float* __restrict__ g2, const float* __restrict__ c2_prev,
                                  float* __restrict__ cnew, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -572,6 +588,8 @@ __global__ void copy2_fwd_kernel(const float* __restrict__ kpre, long ld_k, cons
                                  float* __restrict__ kgate, float* __restrict__ c2, float* __restrict__ h2,
                                  float* __restrict__ h2drop, int rows, int D, int train, uint64_t seed,
                                  long drop_base) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -594,6 +612,8 @@ __global__ void copy2_bwd_kernel(const float* __restrict__ dh2_carry, const floa
                                  float* __restrict__ dg2, float* __restrict__ dkpre, float* __restrict__ dsel,
                                  float* __restrict__ dcnew, int rows, int D, int train, uint64_t seed,
                                  long drop_base) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -614,6 +634,8 @@ __global__ void copy2_bwd_kernel(const float* __restrict__ dh2_carry, const floa
 __global__ void copy1_bwd_kernel(const float* __restrict__ dcnew, const float* __restrict__ g2,
                                  const float* __restrict__ c2_prev, float* __restrict__ dg2,
                                  float* __restrict__ dc2_carry, int rows, int D) {
+  pdl_trigger();
+  pdl_wait();
   const long total = (long)rows * D;
   for (long x = (long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long)gridDim.x * blockDim.x) {
     const int d = (int)(x % D);
@@ -749,23 +771,20 @@ int lstm_fwd(const float* pre, long ld_pre, const float* c_prev, const float* h_
              float* c_out, float* h_out, long ld_h, int rows, int D, const int64_t* len, int t, float* seq_h,
              float* seq_m, long seq_ld, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  lstm_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
-      pre, ld_pre, c_prev, h_prev, gates, c_out, h_out, ld_h, rows, D, len, t, seq_h, seq_m, seq_ld);
+  SET_CHECK_CUDA(launch_chain(lstm_fwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, pre, ld_pre, c_prev, h_prev, gates, c_out, h_out, ld_h, rows, D, len, t, seq_h, seq_m, seq_ld));
   LAUNCH_OK();
 }
 int lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, const float* dh, long ld_dh,
              const float* dh_b, float* dc_carry, float* dgates, int rows, int D, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  lstm_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(gates, c_prev, c_cur, dh, ld_dh,
-                                                                            dh_b, dc_carry, dgates, rows, D);
+  SET_CHECK_CUDA(launch_chain(lstm_bwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, gates, c_prev, c_cur, dh, ld_dh, dh_b, dc_carry, dgates, rows, D));
   LAUNCH_OK();
 }
 int enc_lstm_bwd(const float* gates, const float* c_prev, const float* c_cur, float* dh_run, float* dc_run,
                  const float* dseq_h, const float* dseq_m, long seq_ld, const float* dh_last,
                  const int64_t* len, int t, float* dgates, int rows, int D, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  enc_lstm_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
-      gates, c_prev, c_cur, dh_run, dc_run, dseq_h, dseq_m, seq_ld, dh_last, len, t, dgates, rows, D);
+  SET_CHECK_CUDA(launch_chain(enc_lstm_bwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, gates, c_prev, c_cur, dh_run, dc_run, dseq_h, dseq_m, seq_ld, dh_last, len, t, dgates, rows, D));
   LAUNCH_OK();
 }
 int bilstm_fwd(const float* hh_pre, const float* xg, const int64_t* len, int s, int reverse, const float* h_prev,
@@ -795,7 +814,7 @@ int attention_fwd(const AttnFwdArgs& a, cudaStream_t s) {
   const int n = a.P > a.R ? a.P : a.R;
   const size_t smem = sizeof(float) * (2 * a.A + n + 40);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  attention_fwd_kernel<<<dim3(a.b, 2), kAttnThreads, smem, s>>>(a);
+  SET_CHECK_CUDA(launch_chain(attention_fwd_kernel, dim3(dim3(a.b, 2)), dim3(kAttnThreads), smem, s, a));
   LAUNCH_OK();
 }
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
@@ -803,34 +822,31 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   const int n = a.P > a.R ? a.P : a.R;
   const size_t smem = sizeof(float) * (2 * a.A + 3 * n + 40);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  attention_bwd_kernel<<<dim3(a.b, 2), kAttnThreads, smem, s>>>(a);
+  SET_CHECK_CUDA(launch_chain(attention_bwd_kernel, dim3(dim3(a.b, 2)), dim3(kAttnThreads), smem, s, a));
   LAUNCH_OK();
 }
 int ctx_gate_fwd(const float* s4, long ld_s4, const float* th, long ld_th, float* zst, float* att_cap,
                  long ld_cap, int rows, int D, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  ctx_gate_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(s4, ld_s4, th, ld_th, zst,
-                                                                                att_cap, ld_cap, rows, D);
+  SET_CHECK_CUDA(launch_chain(ctx_gate_fwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, s4, ld_s4, th, ld_th, zst, att_cap, ld_cap, rows, D));
   LAUNCH_OK();
 }
 int ctx_gate_bwd(const float* zst, const float* datt_cap, long ld_dcap, float* dz_out, float* dtc_out,
                  long ld_ds2, float* dsc, int rows, int D, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  ctx_gate_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(zst, datt_cap, ld_dcap, dz_out,
-                                                                                dtc_out, ld_ds2, dsc, rows, D);
+  SET_CHECK_CUDA(launch_chain(ctx_gate_bwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, zst, datt_cap, ld_dcap, dz_out, dtc_out, ld_ds2, dsc, rows, D));
   LAUNCH_OK();
 }
 int copy1_fwd(float* g2, const float* c2_prev, float* cnew, int rows, int D, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  copy1_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(g2, c2_prev, cnew, rows, D);
+  SET_CHECK_CUDA(launch_chain(copy1_fwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, g2, c2_prev, cnew, rows, D));
   LAUNCH_OK();
 }
 int copy2_fwd(const float* kpre, long ld_k, const float* g2, const float* sel, const float* cnew, float* kgate,
               float* c2, float* h2, float* h2drop, int rows, int D, int train, uint64_t seed, long drop_base,
               cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  copy2_fwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
-      kpre, ld_k, g2, sel, cnew, kgate, c2, h2, h2drop, rows, D, train, seed, drop_base);
+  SET_CHECK_CUDA(launch_chain(copy2_fwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, kpre, ld_k, g2, sel, cnew, kgate, c2, h2, h2drop, rows, D, train, seed, drop_base));
   LAUNCH_OK();
 }
 int copy2_bwd(const float* dh2_carry, const float* dh2drop_raw, const float* dc2_carry, const float* g2,
@@ -838,16 +854,13 @@ int copy2_bwd(const float* dh2_carry, const float* dh2drop_raw, const float* dc2
               float* dkpre, float* dsel, float* dcnew, int rows, int D, int train, uint64_t seed, long drop_base,
               cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  copy2_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(
-      dh2_carry, dh2drop_raw, dc2_carry, g2, c2, kgate, sel, cnew, dg2, dkpre, dsel, dcnew, rows, D, train, seed,
-      drop_base);
+  SET_CHECK_CUDA(launch_chain(copy2_bwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, dh2_carry, dh2drop_raw, dc2_carry, g2, c2, kgate, sel, cnew, dg2, dkpre, dsel, dcnew, rows, D, train, seed, drop_base));
   LAUNCH_OK();
 }
 int copy1_bwd(const float* dcnew, const float* g2, const float* c2_prev, float* dg2, float* dc2_carry, int rows,
               int D, cudaStream_t s) {
   if (rows <= 0) return SET_OK;
-  copy1_bwd_kernel<<<blocks_for((long)rows * D, kThreads), kThreads, 0, s>>>(dcnew, g2, c2_prev, dg2, dc2_carry,
-                                                                             rows, D);
+  SET_CHECK_CUDA(launch_chain(copy1_bwd_kernel, dim3(blocks_for((long)rows * D, kThreads)), dim3(kThreads), 0, s, dcnew, g2, c2_prev, dg2, dc2_carry, rows, D));
   LAUNCH_OK();
 }
 int dropout_fwd(const float* x, float* out, int rows, int D, int train, uint64_t seed, uint32_t site,

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #define SET_OK 0
 #define SET_ERR_ARG 1
@@ -42,6 +45,35 @@ extern "C" void set_count_launch(int n);  // bumps the library-wide kernel-launc
   } while (0)
 
 namespace set {
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch.  The decode step is a chain of short dependent kernels; each
+// kernel of the chain is launched with the programmatic-serialization attribute, signals its
+// dependents at entry (pdl_trigger) and blocks (pdl_wait) only where it first touches data the
+// previous kernels produce.  What precedes the wait -- barrier/TMEM set-up and, in the GEMM, the
+// TMA stream of the constant weight operand -- overlaps the tail of the previous kernels.
+// Rules: (1) every kernel launched through launch_chain() executes pdl_wait() before it reads or
+// writes anything a predecessor touches; (2) kernels that WRITE weights (optimizer, transposes)
+// never call pdl_trigger(), so a prefetching GEMM can never run beside them.
+// ---------------------------------------------------------------------------------
+extern int g_pdl;   // 1: chain launches carry the attribute (default; SET_PDL=0 disables)
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 constexpr float kNegFill = -1e10f;  // editnet.py:374 masked_fill value
 

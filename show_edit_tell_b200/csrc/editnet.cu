@@ -223,7 +223,7 @@ int encode_prev(Ctx& c, const int64_t* prev, const int64_t* prev_len) {
     float* pre = s.enc_gates + (size_t)t * B * 4 * D;   // pre-activations, converted in place by lstm_fwd
     GemmProblem p = gemm_problem(B, 4 * D, pre, 4 * D);
     if (t > 0) gemm_add_seg(p, s.enc_h + (size_t)t * B * D, D, w.enc_h2h_w, D, D);
-    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh;
+    p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh; p.w_const = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
     SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
                            s.enc_gates + (size_t)t * B * 4 * D, s.enc_c + (size_t)(t + 1) * B * D,
@@ -311,6 +311,7 @@ int project_words(Ctx& c, int t0, int nt) {
   gemm_add_seg(p[2], s.emb_all + r0 * D, D, w.ca_tc_w, 2 * D, D);
   p[2].bias = w.ca_tc_b;
   p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = c.fresh;
+  p[0].w_const = p[1].w_const = p[2].w_const = 1;
   return gemm_group(kNT, p, 3, c.st);
 }
 
@@ -333,7 +334,7 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
       gemm_add_seg(p, h2prev, D, w.al_wih + 2 * D, 3 * D + F, D);
       gemm_add_seg(p, s.X2 + (size_t)(t - 1) * B * LX2, LX2, w.al_whh, D, D);
     }
-    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh;
+    p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh; p.w_const = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
     SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
                            s.c1 + (size_t)(t + 1) * B * D, X2t, LX2, b, D, nullptr, 0, nullptr, nullptr, 0, st));
@@ -354,7 +355,7 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     gemm_add_seg(p[4], X2t, LX2, w.cl_x2h_w, LX2, D);
     if (t > 0) gemm_add_seg(p[4], h2prev, D, w.cl_h2h_w, D, D);
     p[4].bias = w.cl_x2h_b; p[4].bias2 = w.cl_h2h_b;
-    for (int k = 0; k < 5; ++k) p[k].c_zeroed = c.fresh;
+    for (int k = 0; k < 5; ++k) { p[k].c_zeroed = c.fresh; p[k].w_const = 1; }
     SET_PROPAGATE(gemm_group(kNT, p, 5, st));
   }
   {
@@ -383,20 +384,21 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     gemm_add_seg(p[2], s.sel + (size_t)t * B * D, D, w.cl_gcm_w, D, D);
     p[2].bias = w.cl_gcm_b; p[2].bias2 = w.cl_gcn_b;
     p[0].c_zeroed = p[1].c_zeroed = p[2].c_zeroed = c.fresh;
+    p[0].w_const = p[1].w_const = p[2].w_const = 1;
     SET_PROPAGATE(gemm_group(kNT, p, 3, st));
     SET_PROPAGATE(ctx_gate_fwd(s4t, 3 * D, s2t + 2 * A + D, LS2, s.zst + (size_t)t * B * 3 * D, X2t + D, LX2, b, D, st));
   }
   {
     GemmProblem p = gemm_problem(b, 4 * D, g2t, 4 * D);      // x2h[:, D:] [att_cap | att_img], :272
     gemm_add_seg(p, X2t + D, LX2, w.cl_x2h_w + D, LX2, D + F);
-    p.beta = 1;
+    p.beta = 1; p.w_const = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
     SET_PROPAGATE(copy1_fwd(g2t, s.c2 + (size_t)t * B * D, s.cnew + (size_t)t * B * D, b, D, st));
   }
   {
     GemmProblem p = gemm_problem(b, D, s4t + 2 * D, 3 * D);  // gate_cnew(c_new), :281
     gemm_add_seg(p, s.cnew + (size_t)t * B * D, D, w.cl_gcn_w, D, D);
-    p.beta = 1;
+    p.beta = 1; p.w_const = 1;
     SET_PROPAGATE(gemm(kNT, p, st));
     SET_PROPAGATE(copy2_fwd(s4t + 2 * D, 3 * D, g2t, s.sel + (size_t)t * B * D, s.cnew + (size_t)t * B * D,
                             s.kgate + (size_t)t * B * D, s.c2 + (size_t)(t + 1) * B * D,
@@ -442,11 +444,13 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   auto dx = [&](GemmProblem& p, const float* dY, long ldy, const float* W, const float* WTp, int O, int I, int c0) {
     if (use_wt) gemm_add_seg(p, dY, ldy, WTp + (size_t)c0 * O, O, O);
     else gemm_add_seg(p, dY, ldy, W + c0, I, O);
+    p.w_const = 1;   // W / W^T are not written again before the optimizer step
   };
   {  // d(dropout(h2)) for every step at once: dlogits @ fc.weight
     GemmProblem p = gemm_problem(TB, D, s.dh2raw, D);
     dx(p, dl.p, dl.ld, w.fc_w, s.t_fc, V, D, 0);
     p.a_inner = dl.inner; p.a_ld_inner = dl.ld_inner; p.a_row_len = dl.row_len; p.a_valid_inner = B;
+    p.w_const = 0;   // directly follows the kernels that write W^T
     SET_PROPAGATE(gemm(dxm, p, st));
   }
   SET_PROPAGATE(profile_mark(2, st));
@@ -1020,6 +1024,11 @@ int set_dropout_keep_mask(float* out, size_t n, uint64_t seed, int site, size_t 
 
 int set_gemm_trace(void* buf) {
   gemm_tc_set_trace(reinterpret_cast<unsigned long long*>(buf));
+  return SET_OK;
+}
+
+int set_gemm_trace_seq(void* buf, long stride_u64, int launches) {
+  gemm_tc_set_trace_seq(reinterpret_cast<unsigned long long*>(buf), stride_u64, launches);
   return SET_OK;
 }
 

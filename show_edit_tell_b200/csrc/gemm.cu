@@ -213,6 +213,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, int M, int N
 }  // namespace
 
 int g_backend = 0;              // 0: tensor cores where eligible, 1: CUDA cores only
+int g_pdl = getenv("SET_PDL") ? atoi(getenv("SET_PDL")) : 1;
 long long g_tc_launches = 0, g_simt_launches = 0;
 
 int gemm_group(int mode, const GemmProblem* probs_in, int n, cudaStream_t stream) {

@@ -33,6 +33,8 @@ struct GemmProblem {
   int beta;                              // 1: C += result
   int c_zeroed;                          // caller guarantees C is all-zero (lets split-K skip its memset)
   int act;                               // 0 none, 1 relu, 2 tanh
+  int w_const;                           // the B operands are weights no in-flight kernel writes: the tensor-core
+                                         // kernel may stream them before its grid dependency resolves (common.cuh)
 };
 
 struct GemmGroup {
@@ -56,6 +58,7 @@ inline void gemm_add_seg(GemmProblem& p, const float* A, long lda, const float* 
 // tensor-core path (gemm_tc.cu): launches the eligible problems of a group in one grid
 int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cudaStream_t stream);
 void gemm_tc_set_trace(unsigned long long* buf);
+void gemm_tc_set_trace_seq(unsigned long long* buf, long stride, int launches);
 extern int g_backend;
 extern long long g_tc_launches, g_simt_launches;
 

@@ -9,16 +9,21 @@
 // 2^-22 relative, so results match fp32 FMA accumulation to ~1e-6 (one-pass
 // TF32 misses the 1e-4 parity budget by 10x, 3xTF32 meets it).
 //
-// Either operand may be K-major (global rows = tile rows, reduction contiguous) or MN-major (global
-// rows = reduction index, tile rows contiguous), so x@W^T (NT), dy@W (NN) and dy^T@x (TN) all read
-// the row-major buffers in place; no transposed copies exist.
+// Both operands are K-major (global rows = tile rows, reduction contiguous): x@W^T (NT) reads the row-major
+// buffers in place; callers present dX / dW work in NT form on transposed copies (MN-major tf32 operands
+// read back as zeros with sm_100a descriptors built this way, tools/debug_tc2.py).
 //
 // "swap" mode puts the weight matrix on the 128-row P side and the (<=64..128 row) activation batch
 // on the Q side: that is how the skinny per-step GEMMs (M = batch) fill the tensor core's M=128
 // datapath, with split-K spreading one weight matrix over all 148 SMs.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2-5 = hi/lo converters during the main loop, then the epilogue (TMEM -> registers -> global).
+// The 128-row operand never makes a second trip through shared memory: converter warps read the TMA'd
+// fp32 tile once, split it in registers and write hi | lo into TENSOR memory (tcgen05.st), from where the
+// MMA takes its A operand; only the small Q tile is split in place in shared memory.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = hi/lo converters
+// (groups of 4 warps alternate K-blocks) during the main loop, then the epilogue (TMEM -> registers ->
+// shared -> global).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,7 +39,13 @@ namespace {
 
 constexpr int kBlockK = 32;        // fp32 per smem row: 128 B = one swizzle span
 constexpr int kTileP = 128;        // UMMA M
-constexpr int kConvWarps = 8;       // hi/lo converters (two per TMEM lane quarter), also the epilogue warps
+#ifndef SET_TC_CONV_WARPS
+#define SET_TC_CONV_WARPS 8
+#endif
+constexpr int kConvWarps = SET_TC_CONV_WARPS;   // hi/lo converters, also the epilogue warps
+constexpr int kConvGroups = kConvWarps / 4;     // a group = 4 warps = the 4 TMEM lane quarters; K-block i belongs to
+                                                // group i % kConvGroups, so the groups' latency chains overlap
+constexpr int kGT = 128;                        // threads per converter group
 constexpr int kThreadsTc = 64 + 32 * kConvWarps;
 
 struct TcParams {
@@ -42,7 +53,6 @@ struct TcParams {
   CUtensorMap mapQ[4];
   int K[4];
   int nseg;
-  int p_mn, q_mn;                  // 1: operand is MN-major in global memory
   int Pr, Qr;                      // row extents of the two operands
   int swap;                        // 0: (m,n) = (p,q);  1: (m,n) = (q,p)
   int split_k;
@@ -51,7 +61,7 @@ struct TcParams {
   const float* bias; const float* bias2;
   const float* add; long ldadd; int add_mod;
   int beta, act;
-  int a_tmem;                      // 1: the P operand is fed to the MMA from tensor memory (hi/lo written by tcgen05.st)
+  int pre_p, pre_q;                // operand is a constant weight: its first pipeline stages load before pdl_wait()
   unsigned idesc_xor;              // debugging aid (SET_TC_IDESC_XOR)
   unsigned long long* trace;       // debugging aid: per-phase %globaltimer stamps of CTA 0 (SET_TC_TRACE)
 };
@@ -64,6 +74,13 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TC_STAMP(slot)                                                         \
   do {                                                                         \
     if (prm.trace && blockIdx.x == 0) prm.trace[slot] = gtimer();              \
+  } while (0)
+
+// per-K-block SM-clock stamps of CTA 0 (slots: 0 producer issued Q, 1 producer issued P, 2 converter saw Q,
+// 3 converter saw P, 4 converter done, 5 MMA saw converted block, 6 MMA issued)
+#define KB_STAMP(i, slot)                                                                       \
+  do {                                                                                          \
+    if (prm.trace && blockIdx.x == 0 && (i) < 48) prm.trace[400 + 8 * (i) + (slot)] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,14 +119,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes,
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // A operand from tensor memory: [128 lanes] x [8 columns of tf32] at `tmem_a`
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -126,8 +135,19 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
-constexpr uint32_t kTmemABase = 128;   // columns [0,128): accumulator; [128 + 64*stage, +64): P_hi | P_lo of a stage
+// tensor-memory columns [0,QN): accumulator; [QN + 64*slot, +64): P_hi | P_lo of a Q/TMEM slot
 
+// one lane of a converged warp; ptxas then treats the guarded block as warp-uniform (tcgen05.mma issues
+// straight from uniform registers, no per-lane replay loop around it)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -146,11 +166,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 template <int QN>
 struct TcCfg {
-  static constexpr int kStages = (QN <= 64) ? 4 : 3;
-  static constexpr int kPBytes = kTileP * 128;              // one P tile (hi or lo)
+  // Two rings.  P: raw fp32 tiles of the 128-row operand; a K-block of P is converted straight into tensor
+  // memory, so the ring only has to cover the HBM latency -- it is the deep one (Little: 148 SMs x kNP x 16 KB
+  // in flight ~ 19 MB >= 6.5 TB/s x 2 us).  Q: hi | lo tiles the MMA reads from shared memory, paired with the
+  // tensor-memory slots of P_hi | P_lo; both are released by the MMA's commit.
+#ifndef SET_TC_NQ64
+#define SET_TC_NQ64 6
+#define SET_TC_NP64 6
+#endif
+  static constexpr int kNQ = (QN <= 64) ? SET_TC_NQ64 : 3;
+  static constexpr int kNP = (QN <= 64) ? SET_TC_NP64 : 6;
+  static constexpr int kPBytes = kTileP * 128;
   static constexpr int kQBytes = QN * 128;
-  static constexpr int kStageBytes = 2 * kPBytes + 2 * kQBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kQSlot = 2 * kQBytes;
+  static constexpr int kRingBytes = kNP * kPBytes + kNQ * kQSlot;
+  static constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int G>
@@ -166,15 +196,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   int pi = 0;
   while (pi + 1 < grp.n && (int)blockIdx.x >= grp.cta_start[pi + 1]) ++pi;
   const TcParams& prm = grp.p[pi];
-  constexpr int S = Cfg::kStages;
+  constexpr int NP = Cfg::kNP, NQ = Cfg::kNQ;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + S * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto conv_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
-  const uint32_t accum_bar = bar_base + 8u * (3 * S);
-  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 1);
+  const uint32_t q_base = base + NP * Cfg::kPBytes;
+  const uint32_t bar_base = base + Cfg::kRingBytes;
+  auto p_full = [&](int s) { return bar_base + 8u * s; };
+  auto q_full = [&](int s) { return bar_base + 8u * (NP + s); };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (NP + NQ + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (NP + 2 * NQ + s); };
+  const uint32_t accum_bar = bar_base + 8u * (NP + 3 * NQ);
+  const uint32_t tmem_slot = bar_base + 8u * (NP + 3 * NQ + 1);
   uint8_t* gen_base = smem_dyn + (base - smem_u32(smem_dyn));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,17 +227,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   const int nkb = kb_end - kb_begin;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), kConvWarps);
+    for (int s = 0; s < NP; ++s) mbar_init(p_full(s), 1);
+    for (int s = 0; s < NQ; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(conv_bar(s), 4);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"(prm.a_tmem ? 512u : (uint32_t)QN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                 : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -214,145 +247,150 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
   if (threadIdx.x == 64) TC_STAMP(1);
 
+  pdl_trigger();
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0 && nkb > 0) {
-      int seg = 0, kb_in_seg = kb_begin;
-      while (kb_in_seg >= (prm.K[seg] + kBlockK - 1) / kBlockK) { kb_in_seg -= (prm.K[seg] + kBlockK - 1) / kBlockK; ++seg; }
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % S;
-        const uint32_t ph = (uint32_t)(i / S) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t st = base + s * Cfg::kStageBytes;
-        mbar_expect_tx(full_bar(s), Cfg::kPBytes + Cfg::kQBytes);
-        const int k0 = kb_in_seg * kBlockK;
-        if (!prm.p_mn) {
-          tma_load_2d(st, &prm.mapP[seg], full_bar(s), k0, p0);
-        } else {
-#pragma unroll
-          for (int c = 0; c < kTileP / 32; ++c) tma_load_2d(st + c * 4096, &prm.mapP[seg], full_bar(s), p0 + 32 * c, k0);
+    if (nkb > 0) {   // warp-uniform control flow; one elected lane issues the bulk copies
+      struct KbIter { int seg, kb; };
+      auto nkb_of = [&](int sg) { return (prm.K[sg] + kBlockK - 1) / kBlockK; };
+      auto advance = [&](KbIter& it) { if (++it.kb >= nkb_of(it.seg)) { it.kb = 0; ++it.seg; } };
+      KbIter it0{0, kb_begin};
+      while (it0.kb >= nkb_of(it0.seg)) { it0.kb -= nkb_of(it0.seg); ++it0.seg; }
+      auto load_p = [&](int j, const KbIter& it) {   // K-block j of this CTA
+        const int s = j % NP;
+        if (elect_one()) {
+          mbar_expect_tx(p_full(s), Cfg::kPBytes);
+          tma_load_2d(base + s * Cfg::kPBytes, &prm.mapP[it.seg], p_full(s), it.kb * kBlockK, p0);
+          KB_STAMP(j, 1);
         }
-        const uint32_t sq = st + 2 * Cfg::kPBytes;
-        if (!prm.q_mn) {
-          tma_load_2d(sq, &prm.mapQ[seg], full_bar(s), k0, q0);
-        } else {
-#pragma unroll
-          for (int c = 0; c < QN / 32; ++c) tma_load_2d(sq + c * 4096, &prm.mapQ[seg], full_bar(s), q0 + 32 * c, k0);
+        __syncwarp();
+      };
+      auto load_q = [&](int j, const KbIter& it) {
+        const int s = j % NQ;
+        if (elect_one()) {
+          mbar_expect_tx(q_full(s), Cfg::kQBytes);
+          tma_load_2d(q_base + s * Cfg::kQSlot, &prm.mapQ[it.seg], q_full(s), it.kb * kBlockK, q0);
+          KB_STAMP(j, 0);
         }
-        if (++kb_in_seg >= (prm.K[seg] + kBlockK - 1) / kBlockK) { kb_in_seg = 0; ++seg; }
+        __syncwarp();
+      };
+      // Fill both (empty) rings; the operand that is a constant weight goes out before the grid
+      // dependency resolves, i.e. while the previous kernels of the chain are still running.
+      const int np0 = nkb < NP ? nkb : NP, nq0 = nkb < NQ ? nkb : NQ;
+      KbIter itp = it0, itq = it0;
+      if (prm.pre_p) for (int j = 0; j < np0; ++j) { load_p(j, itp); advance(itp); }
+      if (prm.pre_q) for (int j = 0; j < nq0; ++j) { load_q(j, itq); advance(itq); }
+      pdl_wait();
+      if (!prm.pre_p) for (int j = 0; j < np0; ++j) { load_p(j, itp); advance(itp); }
+      if (!prm.pre_q) for (int j = 0; j < nq0; ++j) { load_q(j, itq); advance(itq); }
+      // Steady state: the MMA's commit for K-block j - NQ frees Q/TMEM slot j % NQ -- and, a fortiori, the P
+      // slot of K-block j - NQ (its conversion preceded that MMA), which K-block j - NQ + NP reuses.
+      for (int j = NQ; j < nkb; ++j) {
+        mbar_wait(empty_bar(j % NQ), ((uint32_t)(j / NQ) & 1u) ^ 1u);
+        load_q(j, itq); advance(itq);
+        const int jp = j - NQ + NP;
+        if (jp < nkb) { load_p(jp, itp); advance(itp); }
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0 && nkb > 0) {
-      // instruction descriptor: D=f32, A=B=tf32, majors, N, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(prm.p_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(prm.q_mn ? 1 : 0) << 16) | ((uint32_t)(QN >> 3) << 17) |
-                             ((uint32_t)(kTileP >> 4) << 24);
-      const uint32_t idesc_final = idesc ^ prm.idesc_xor;
-      // per K-step (8 tf32) descriptor advance and strides
-      const uint32_t p_step = prm.p_mn ? 1024u : 32u, q_step = prm.q_mn ? 1024u : 32u;
-      const uint32_t p_lbo = prm.p_mn ? 4096u : 16u, q_lbo = prm.q_mn ? 4096u : 16u;
+    if (nkb > 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N, M=128
+      const uint32_t idesc = ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QN >> 3) << 17) |
+                              ((uint32_t)(kTileP >> 4) << 24)) ^ prm.idesc_xor;
+      // the whole warp walks the K-blocks (warp-uniform control flow); one elected lane issues
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S;
-        const uint32_t ph = (uint32_t)(i / S) & 1u;
-        mbar_wait(conv_bar(s), ph);
+        const int s = i % NQ;
+        mbar_wait(conv_bar(s), (uint32_t)(i / NQ) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = base + s * Cfg::kStageBytes;
-        const uint32_t p_hi = st, p_lo = st + Cfg::kPBytes, q_hi = st + 2 * Cfg::kPBytes,
-                       q_lo = st + 2 * Cfg::kPBytes + Cfg::kQBytes;
+        if (elect_one()) {
+          KB_STAMP(i, 5);
+          const uint32_t q_hi = q_base + s * Cfg::kQSlot, q_lo = q_hi + Cfg::kQBytes;
+          const uint64_t b_hi0 = umma_desc(q_hi, 16u, 1024u), b_lo0 = umma_desc(q_lo, 16u, 1024u);
+          const uint32_t ta0 = tmem_base + (uint32_t)QN + (uint32_t)s * 64u;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 8; ++k) {
-          const uint64_t a_hi = umma_desc(p_hi + k * p_step, p_lbo, 1024u);
-          const uint64_t a_lo = umma_desc(p_lo + k * p_step, p_lbo, 1024u);
-          const uint64_t b_hi = umma_desc(q_hi + k * q_step, q_lbo, 1024u);
-          const uint64_t b_lo = umma_desc(q_lo + k * q_step, q_lbo, 1024u);
-          if (prm.a_tmem) {
-            const uint32_t ta_hi = tmem_base + kTmemABase + (uint32_t)s * 64u + (uint32_t)k * 8u;
-            umma_tf32_ts(tmem_base, ta_hi + 32u, b_hi, idesc_final, (i > 0 || k > 0) ? 1u : 0u);
-            umma_tf32_ts(tmem_base, ta_hi, b_lo, idesc_final, 1u);
-            umma_tf32_ts(tmem_base, ta_hi, b_hi, idesc_final, 1u);
-          } else {
-            umma_tf32(tmem_base, a_lo, b_hi, idesc_final, (i > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(tmem_base, a_hi, b_lo, idesc_final, 1u);
-            umma_tf32(tmem_base, a_hi, b_hi, idesc_final, 1u);
+          for (int k = 0; k < kBlockK / 8; ++k) {
+            // +32 bytes along K = +2 in the descriptor's (addr >> 4) field; +8 tensor-memory columns
+            const uint64_t b_hi = b_hi0 + (uint64_t)(2 * k), b_lo = b_lo0 + (uint64_t)(2 * k);
+            const uint32_t ta_hi = ta0 + (uint32_t)k * 8u;
+            umma_tf32_ts(tmem_base, ta_hi + 32u, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);   // P_lo * Q_hi
+            umma_tf32_ts(tmem_base, ta_hi, b_lo, idesc, 1u);                                 // P_hi * Q_lo
+            umma_tf32_ts(tmem_base, ta_hi, b_hi, idesc, 1u);                                 // P_hi * Q_hi
           }
+          umma_commit(empty_bar(s));   // Q slot + tensor-memory slot reusable once these MMAs retire
+          KB_STAMP(i, 6);
         }
-        umma_commit(empty_bar(s));   // smem slot reusable once these MMAs retire
+        __syncwarp();
       }
-      umma_commit(accum_bar);
+      if (elect_one()) umma_commit(accum_bar);
+      __syncwarp();
     }
   } else {
     // ============================== converters, then epilogue ==============================
     const int ct = threadIdx.x - 64;   // 0 .. 32*kConvWarps-1
     constexpr int kCT = 32 * kConvWarps;
-    const int khalf = (warp - 2) >> 2;  // which 16-column half of the K-block this warp converts (A-from-TMEM)
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % S;
-      const uint32_t ph = (uint32_t)(i / S) & 1u;
-      mbar_wait(full_bar(s), ph);
-      if (ct == 0 && i == 0) TC_STAMP(2);
-      uint8_t* st = gen_base + s * Cfg::kStageBytes;
-      float4* p_hi = reinterpret_cast<float4*>(st);
-      float4* p_lo = reinterpret_cast<float4*>(st + Cfg::kPBytes);
-      float4* q_hi = reinterpret_cast<float4*>(st + 2 * Cfg::kPBytes);
-      float4* q_lo = reinterpret_cast<float4*>(st + 2 * Cfg::kPBytes + Cfg::kQBytes);
+    const int grp_id = (warp - 2) >> 2;  // converter group of this warp
+    const int gt = ct & (kGT - 1);       // thread index within the group
+    for (int i = grp_id; i < nkb; i += kConvGroups) {
+      const int sq = i % NQ, sp = i % NP;
       auto split = [](float x, float& hi, float& lo) {
         hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
         lo = x - hi;
       };
-      if (prm.a_tmem) {
-        // P (the 128-row operand) goes to tensor memory: this thread owns tile row `prow` = its TMEM lane,
-        // reads the row's 32 fp32 out of the 128B-swizzled tile (16-byte chunk c of row r sits at chunk
-        // c ^ (r & 7)) and stores hi | lo as 2 x 32 columns.  No shared-memory write-back, and the MMA
-        // no longer re-reads P from shared memory -- the two largest smem streams of the SS form.
-        const int prow = (warp & 3) * 32 + lane;
+      // Q: hi written back in place over the TMA'd tile, lo to the sibling tile
+      mbar_wait(q_full(sq), (uint32_t)(i / NQ) & 1u);
+      if (gt == 0) KB_STAMP(i, 2);
+      float4* q_hi = reinterpret_cast<float4*>(gen_base + (q_base - base) + sq * Cfg::kQSlot);
+      float4* q_lo = reinterpret_cast<float4*>(gen_base + (q_base - base) + sq * Cfg::kQSlot + Cfg::kQBytes);
+#pragma unroll
+      for (int j = 0; j < Cfg::kQBytes / 16 / kGT; ++j) {
+        const float4 v = q_hi[gt + kGT * j];
+        float4 h, l;
+        split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
+        q_hi[gt + kGT * j] = h;
+        q_lo[gt + kGT * j] = l;
+      }
+      // P (the 128-row operand) goes to tensor memory: this thread owns tile row `prow` = its TMEM lane, reads
+      // the row's 32 fp32 out of the 128B-swizzled tile (16-byte chunk c of row r sits at chunk c ^ (r & 7)) and
+      // stores hi | lo as 2 x 32 columns.  No shared-memory write-back, and the MMA never reads P from shared
+      // memory.
+      mbar_wait(p_full(sp), (uint32_t)(i / NP) & 1u);
+      if (gt == 0) KB_STAMP(i, 3);
+      if (ct == 0 && i == 0) TC_STAMP(2);
+      const float4* p_raw = reinterpret_cast<const float4*>(gen_base + sp * Cfg::kPBytes);
+      const int prow = (warp & 3) * 32 + lane;
+      const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)QN + (uint32_t)sq * 64u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int cch = khalf * 4 + cc;
-          const float4 v = p_hi[prow * 8 + (cch ^ (prow & 7))];
+          const int cch = half * 4 + cc;
+          const float4 v = p_raw[prow * 8 + (cch ^ (prow & 7))];
           float h, l;
           split(v.x, h, l); hi[cc * 4 + 0] = __float_as_uint(h); lo[cc * 4 + 0] = __float_as_uint(l);
           split(v.y, h, l); hi[cc * 4 + 1] = __float_as_uint(h); lo[cc * 4 + 1] = __float_as_uint(l);
           split(v.z, h, l); hi[cc * 4 + 2] = __float_as_uint(h); lo[cc * 4 + 2] = __float_as_uint(l);
           split(v.w, h, l); hi[cc * 4 + 3] = __float_as_uint(h); lo[cc * 4 + 3] = __float_as_uint(l);
         }
-        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemABase + (uint32_t)s * 64u +
-                            (uint32_t)khalf * 16u;
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 32u, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < Cfg::kPBytes / 16 / kCT; ++j) {
-          const float4 v = p_hi[ct + kCT * j];
-          float4 h, l;
-          split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
-          p_hi[ct + kCT * j] = h;
-          p_lo[ct + kCT * j] = l;
-        }
+        tmem_st16(ta + (uint32_t)half * 16u, hi);
+        tmem_st16(ta + 32u + (uint32_t)half * 16u, lo);
       }
-#pragma unroll
-      for (int j = 0; j < Cfg::kQBytes / 16 / kCT; ++j) {
-        const float4 v = q_hi[ct + kCT * j];
-        float4 h, l;
-        split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
-        q_hi[ct + kCT * j] = h;
-        q_lo[ct + kCT * j] = l;
-      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(conv_bar(s));
+      if (lane == 0) mbar_arrive(conv_bar(sq));
+      if (gt == 0) KB_STAMP(i, 4);
       if (ct == 0 && i == 0) TC_STAMP(3);
-      if (ct == 0 && i == nkb - 1) TC_STAMP(4);
+      if (i == nkb - 1 && gt == 0) TC_STAMP(4);
     }
     // ---- epilogue
     if (nkb > 0) {
       mbar_wait(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    pdl_wait();   // C, `add` and c_row_len may be produced by the preceding kernels
     if (ct == 0) TC_STAMP(5);
     // Accumulator -> registers -> shared (the pipeline stages are idle now).  The tile is staged in the
     // orientation of the OUTPUT rows (transposed for swap mode) so that the second phase reads float4
@@ -444,8 +482,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   if (threadIdx.x == 64) TC_STAMP(8);
   if (prm.trace && threadIdx.x == 0 && blockIdx.x < 1000) prm.trace[17 + 2 * blockIdx.x] = gtimer();   // per-CTA end
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(prm.a_tmem ? 512u : (uint32_t)QN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -493,6 +530,8 @@ bool make_map(CUtensorMap* m, const float* ptr, long rows, long cols, long ld, i
 }
 
 unsigned long long* g_tc_trace = nullptr;
+long g_tc_trace_stride = 0;      // > 0: launch n of a traced sequence stamps buf + n * stride (u64 units)
+int g_tc_trace_left = 0;
 
 bool aligned_ok(const float* p, long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 4) == 0; }
 
@@ -502,11 +541,9 @@ bool aligned_ok(const float* p, long ld) { return (reinterpret_cast<uintptr_t>(p
 // (caller falls back to the CUDA-core kernel).  `QN` is the Q-tile width chosen for the whole group.
 static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   if (g.nseg < 1 || g.M <= 0 || g.N <= 0) return false;
-  // MN-major operands (the NN / TN forms) are wired through the kernel but read back as zeros on
-  // sm_100a with these descriptors (tools/debug_tc2.py) -- until that is understood only the
-  // K-major/K-major (NT) form runs on tensor cores; callers present NN/TN work in NT form on
-  // transposed copies (editnet.cu backward_core) or fall back to the CUDA-core kernel.
-  if (mode != kNT && getenv("SET_TC_ALLOW_MN") == nullptr) return false;
+  // only the K-major/K-major (NT) form runs on tensor cores; NN/TN work arrives in NT form on transposed
+  // copies (editnet.cu backward_core) or falls back to the CUDA-core kernel
+  if (mode != kNT) return false;
   if (g.a_inner > 0 || g.a_row_len) return false;         // two-level / masked A rows stay on the CUDA-core path
   long ktot = 0;
   for (int s = 0; s < g.nseg; ++s) {
@@ -515,30 +552,19 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   }
   if (ktot < 64) return false;
   memset(&prm, 0, sizeof(prm));
-  // operand roles: the A-side (M rows) and the B-side (N rows) of the logical GEMM
-  //   kNT: A[m][k] K-major,   B[n][k] K-major
-  //   kNN: A[m][k] K-major,   B[k][n] MN-major
-  //   kTN: A[k][m] MN-major,  B[k][n] MN-major
-  const int a_mn = (mode == kTN), b_mn = (mode != kNT);
   // skinny M: weights (B side, N rows) take the 128-row P role
   const bool swap = (g.M <= QN && g.N > g.M);
   const int Pr = swap ? g.N : g.M, Qr = swap ? g.M : g.N;
   if (swap && (g.c_inner > 0)) return false;
   prm.swap = swap; prm.Pr = Pr; prm.Qr = Qr;
-  prm.p_mn = swap ? b_mn : a_mn;
-  prm.q_mn = swap ? a_mn : b_mn;
   prm.nseg = g.nseg;
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
     prm.K[s] = sg.K;
     const float* Pp = swap ? sg.B : sg.A; const long Pld = swap ? sg.ldb : sg.lda;
     const float* Qp = swap ? sg.A : sg.B; const long Qld = swap ? sg.lda : sg.ldb;
-    bool ok;
-    if (!prm.p_mn) ok = make_map(&prm.mapP[s], Pp, Pr, sg.K, Pld, kBlockK, kTileP);
-    else ok = make_map(&prm.mapP[s], Pp, sg.K, Pr, Pld, 32, kBlockK);
-    if (!prm.q_mn) ok = ok && make_map(&prm.mapQ[s], Qp, Qr, sg.K, Qld, kBlockK, QN);
-    else ok = ok && make_map(&prm.mapQ[s], Qp, sg.K, Qr, Qld, 32, kBlockK);
-    if (!ok) return false;
+    if (!make_map(&prm.mapP[s], Pp, Pr, sg.K, Pld, kBlockK, kTileP)) return false;
+    if (!make_map(&prm.mapQ[s], Qp, Qr, sg.K, Qld, kBlockK, QN)) return false;
   }
   prm.tiles_p = (Pr + kTileP - 1) / kTileP;
   prm.tiles_q = (Qr + QN - 1) / QN;
@@ -548,11 +574,9 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   prm.bias = g.bias; prm.bias2 = g.bias2; prm.add = g.add; prm.ldadd = g.ldadd; prm.add_mod = g.add_mod;
   prm.beta = g.beta; prm.act = g.act;
   { const char* e = getenv("SET_TC_IDESC_XOR"); prm.idesc_xor = e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }
-  prm.trace = g_tc_trace;
-  {
-    static const int atmem = getenv("SET_TC_ATMEM") ? atoi(getenv("SET_TC_ATMEM")) : 1;
-    prm.a_tmem = (atmem && !prm.p_mn) ? 1 : 0;
-  }
+  prm.trace = g_tc_trace;   // (a sequence trace advances per launch, see gemm_tc_try_group)
+  prm.pre_p = (g.w_const && swap) ? 1 : 0;
+  prm.pre_q = (g.w_const && !swap) ? 1 : 0;
   return true;
 }
 
@@ -609,25 +633,40 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     taken[idx[k]] = true;
   }
   grp.cta_start[grp.n] = cta;
+  if (g_tc_trace && g_tc_trace_stride > 0) {
+    if (g_tc_trace_left > 0) {
+      // header: [8] grid size, [9] problems in the group, [10] K-blocks per CTA of problem 0
+      for (int k = 0; k < grp.n; ++k) grp.p[k].trace = g_tc_trace;
+      g_tc_trace += g_tc_trace_stride;
+      --g_tc_trace_left;
+    } else {
+      for (int k = 0; k < grp.n; ++k) grp.p[k].trace = nullptr;
+    }
+  }
   auto launch = [&](auto tag) {
     constexpr int G = decltype(tag)::value;
     TcGroup<G> small;
     small.n = grp.n;
     memcpy(small.cta_start, grp.cta_start, sizeof(small.cta_start));
     memcpy(small.p, grp.p, sizeof(TcParams) * grp.n);
-    if (QN == 64) gemm_tc_kernel<64, G><<<cta, kThreadsTc, TcCfg<64>::kSmemBytes, stream>>>(small);
-    else gemm_tc_kernel<128, G><<<cta, kThreadsTc, TcCfg<128>::kSmemBytes, stream>>>(small);
+    if (QN == 64) return launch_chain(gemm_tc_kernel<64, G>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, small);
+    return launch_chain(gemm_tc_kernel<128, G>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, small);
   };
-  if (grp.n == 1) launch(std::integral_constant<int, 1>{});
-  else if (grp.n == 2) launch(std::integral_constant<int, 2>{});
-  else if (grp.n <= 5) launch(std::integral_constant<int, 5>{});
-  else launch(std::integral_constant<int, 8>{});
+  cudaError_t lerr;
+  if (grp.n == 1) lerr = launch(std::integral_constant<int, 1>{});
+  else if (grp.n == 2) lerr = launch(std::integral_constant<int, 2>{});
+  else if (grp.n <= 5) lerr = launch(std::integral_constant<int, 5>{});
+  else lerr = launch(std::integral_constant<int, 8>{});
+  SET_CHECK_CUDA(lerr);
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
   return SET_OK;
 }
 
 // debugging: device buffer of >= 16 u64 that CTA 0 of every following tensor-core launch stamps
-void gemm_tc_set_trace(unsigned long long* buf) { g_tc_trace = buf; }
+void gemm_tc_set_trace(unsigned long long* buf) { g_tc_trace = buf; g_tc_trace_stride = 0; g_tc_trace_left = 0; }
+void gemm_tc_set_trace_seq(unsigned long long* buf, long stride, int launches) {
+  g_tc_trace = buf; g_tc_trace_stride = stride; g_tc_trace_left = launches;
+}
 
 }  // namespace set
