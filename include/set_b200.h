@@ -264,7 +264,8 @@ SET_API int set_gemm_backend(int backend);
 /* debugging: device buffer (>= 16 x uint64) stamped with %globaltimer by CTA 0 of each tensor-core launch */
 SET_API int set_gemm_trace(void* buf);
 /* debugging: the next `launches` tensor-core launches stamp consecutive slices (stride_u64 x uint64 each,
-   >= 16 + 2 * grid) of `buf`: [0..8] phase stamps of CTA 0, [16 + 2c], [17 + 2c] entry/exit time of CTA c */
+   >= 2500) of `buf`: [0..8] phase stamps of CTA 0, [16 + 2c], [17 + 2c] entry/exit time of CTA c < 1000,
+   [2100 + 8k + s] SM-clock stamps of K-block k of CTA 0 */
 SET_API int set_gemm_trace_seq(void* buf, long stride_u64, int launches);
 SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
 /* C = A @ B^T style contraction through the library's GEMM engine (mode 0 NT, 1 NN, 2 TN). */

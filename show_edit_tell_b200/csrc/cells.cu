@@ -18,14 +18,6 @@ inline int blocks_for(long n, int per_block) {
   return (int)b;
 }
 
-// four keep bits for elements idx..idx+3 (idx % 4 == 0)
-__device__ __forceinline__ uint32_t drop_keep4(uint64_t seed, uint32_t site, uint64_t idx) {
-  const uint4 b = drop_bits128(seed, site, idx >> 7);
-  const uint32_t bit = (uint32_t)idx & 127u;
-  const uint32_t w = bit < 64 ? (bit < 32 ? b.x : b.y) : (bit < 96 ? b.z : b.w);
-  return (w >> (bit & 31u)) & 0xFu;
-}
-
 // ------------------------------------------------------------------------ embedding
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ tokens, long tok_ld, long tok_os,
                                  const float* __restrict__ table, int V, float* __restrict__ out, int n_outer,

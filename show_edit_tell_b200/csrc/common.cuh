@@ -140,6 +140,14 @@ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t
   const uint32_t w = bit < 64 ? (bit < 32 ? b.x : b.y) : (bit < 96 ? b.z : b.w);
   return (w >> (bit & 31u)) & 1u;
 }
+// four keep bits for elements idx..idx+3 (idx % 4 == 0)
+__device__ __forceinline__ uint32_t drop_keep4(uint64_t seed, uint32_t site, uint64_t idx) {
+  const uint4 b = drop_bits128(seed, site, idx >> 7);
+  const uint32_t bit = (uint32_t)idx & 127u;
+  const uint32_t w = bit < 64 ? (bit < 32 ? b.x : b.y) : (bit < 96 ? b.z : b.w);
+  return (w >> (bit & 31u)) & 0xFu;
+}
+
 // uniform in [0,1) for sampling; one per (site, idx)
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t site, uint64_t idx) {
   const uint4 b = drop_bits128(seed, site, idx);

@@ -335,9 +335,14 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
       gemm_add_seg(p, s.X2 + (size_t)(t - 1) * B * LX2, LX2, w.al_whh, D, D);
     }
     p.add = s.pre1 + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh; p.w_const = 1;
+    // the LSTM cell rides in the GEMM's epilogue when the tensor-core path takes the problem
+    int fused = 0;
+    p.epi.op = kEpiLstm; p.epi.D = D; p.epi.c_prev = s.c1 + (size_t)t * B * D; p.epi.c_out = s.c1 + (size_t)(t + 1) * B * D;
+    p.epi.h_out = X2t; p.epi.ld_h = LX2; p.epi.gates = pre; p.epi.ld_gates = 4 * D; p.epi_done = &fused;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
-                           s.c1 + (size_t)(t + 1) * B * D, X2t, LX2, b, D, nullptr, 0, nullptr, nullptr, 0, st));
+    if (!fused)
+      SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.c1 + (size_t)t * B * D, nullptr, s.gates1 + (size_t)t * B * 4 * D,
+                             s.c1 + (size_t)(t + 1) * B * D, X2t, LX2, b, D, nullptr, 0, nullptr, nullptr, 0, st));
   }
   {  // everything that consumes h1 in one grouped launch
     GemmProblem p[5];
@@ -392,18 +397,28 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
     GemmProblem p = gemm_problem(b, 4 * D, g2t, 4 * D);      // x2h[:, D:] [att_cap | att_img], :272
     gemm_add_seg(p, X2t + D, LX2, w.cl_x2h_w + D, LX2, D + F);
     p.beta = 1; p.w_const = 1;
+    int fused = 0;   // copy-LSTM stage 1 (gates, c_new) in the epilogue
+    p.epi.op = kEpiCopy1; p.epi.D = D; p.epi.c_prev = s.c2 + (size_t)t * B * D; p.epi.c_out = s.cnew + (size_t)t * B * D;
+    p.epi.gates = g2t; p.epi.ld_gates = 4 * D; p.epi_done = &fused;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(copy1_fwd(g2t, s.c2 + (size_t)t * B * D, s.cnew + (size_t)t * B * D, b, D, st));
+    if (!fused) SET_PROPAGATE(copy1_fwd(g2t, s.c2 + (size_t)t * B * D, s.cnew + (size_t)t * B * D, b, D, st));
   }
   {
     GemmProblem p = gemm_problem(b, D, s4t + 2 * D, 3 * D);  // gate_cnew(c_new), :281
     gemm_add_seg(p, s.cnew + (size_t)t * B * D, D, w.cl_gcn_w, D, D);
     p.beta = 1; p.w_const = 1;
+    int fused = 0;   // copy gate, c2, h2, dropout(h2) in the epilogue
+    p.epi.op = kEpiCopy2; p.epi.D = D; p.epi.gates = g2t; p.epi.ld_gates = 4 * D;
+    p.epi.sel = s.sel + (size_t)t * B * D; p.epi.cnew = s.cnew + (size_t)t * B * D;
+    p.epi.kgate = s.kgate + (size_t)t * B * D; p.epi.c_out = s.c2 + (size_t)(t + 1) * B * D;
+    p.epi.h_out = s.h2 + (size_t)(t + 1) * B * D; p.epi.ld_h = D; p.epi.h2drop = s.h2drop + (size_t)t * B * D;
+    p.epi.train = c.s.train; p.epi.seed = c.seed; p.epi.drop_base = (long)t * B * D; p.epi_done = &fused;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(copy2_fwd(s4t + 2 * D, 3 * D, g2t, s.sel + (size_t)t * B * D, s.cnew + (size_t)t * B * D,
-                            s.kgate + (size_t)t * B * D, s.c2 + (size_t)(t + 1) * B * D,
-                            s.h2 + (size_t)(t + 1) * B * D, s.h2drop + (size_t)t * B * D, b, D, c.s.train, c.seed,
-                            (long)t * B * D, st));
+    if (!fused)
+      SET_PROPAGATE(copy2_fwd(s4t + 2 * D, 3 * D, g2t, s.sel + (size_t)t * B * D, s.cnew + (size_t)t * B * D,
+                              s.kgate + (size_t)t * B * D, s.c2 + (size_t)(t + 1) * B * D,
+                              s.h2 + (size_t)(t + 1) * B * D, s.h2drop + (size_t)t * B * D, b, D, c.s.train, c.seed,
+                              (long)t * B * D, st));
   }
   return SET_OK;
 }

@@ -20,6 +20,22 @@ struct GemmSeg {
   int K;
 };
 
+// Pointwise cell fused behind a skinny (M = batch) GEMM: the CTA that completes a tile's split-K reduction
+// applies it to the finished pre-activations (gemm_tc.cu "fused epilogue").  A 4-gate op makes the kernel
+// compose each 128-row weight tile from the 32-row blocks of the four gates of the same 32 hidden units.
+enum GemmEpiOp { kEpiNone = 0, kEpiLstm = 1, kEpiCopy1 = 2, kEpiCopy2 = 3 };
+struct GemmEpi {
+  int op;
+  int D;                        // hidden size = gate stride along N
+  const float* c_prev;          // lstm, copy1: previous cell state [rows][D]
+  float* c_out;                 // lstm: c;  copy1: c_new;  copy2: c2
+  float* h_out; long ld_h;      // lstm: h;  copy2: h2
+  float* gates; long ld_gates;  // lstm: activated gates out;  copy1: g2 in place (C);  copy2: g2 (o gate, read)
+  const float* sel; const float* cnew;   // copy2
+  float* kgate; float* h2drop;           // copy2
+  int train; unsigned long long seed; long drop_base;
+};
+
 struct GemmProblem {
   int M, N, nseg;
   GemmSeg seg[4];
@@ -33,6 +49,8 @@ struct GemmProblem {
   int beta;                              // 1: C += result
   int c_zeroed;                          // caller guarantees C is all-zero (lets split-K skip its memset)
   int act;                               // 0 none, 1 relu, 2 tanh
+  GemmEpi epi;                           // optional fused cell (tensor-core swap mode only)
+  int* epi_done;                         // set to 1 when the launch applies `epi`; else the caller runs the cell kernel
   int w_const;                           // the B operands are weights no in-flight kernel writes: the tensor-core
                                          // kernel may stream them before its grid dependency resolves (common.cuh)
 };

@@ -46,6 +46,7 @@ constexpr int kConvWarps = SET_TC_CONV_WARPS;   // hi/lo converters, also the ep
 constexpr int kConvGroups = kConvWarps / 4;     // a group = 4 warps = the 4 TMEM lane quarters; K-block i belongs to
                                                 // group i % kConvGroups, so the groups' latency chains overlap
 constexpr int kGT = 128;                        // threads per converter group
+constexpr int kMaxFusedSplit = 6;               // split-K ways the fused epilogue reduces
 constexpr int kThreadsTc = 64 + 32 * kConvWarps;
 
 struct TcParams {
@@ -61,6 +62,14 @@ struct TcParams {
   const float* bias; const float* bias2;
   const float* add; long ldadd; int add_mod;
   int beta, act;
+  int fused;                       // swap mode: split-K partials meet in a scratch slab; the tile's last CTA reduces,
+                                   // adds bias/add/C and applies `epi`
+  int nblk, blk_stride;            // P tile = nblk blocks of 128/nblk rows; block j starts at global row
+                                   // j * blk_stride + tile * (128 / nblk)   (nblk = 4: the four gates of 32 units)
+  float* scratch; int* counters;   // library-owned split-K scratch: one [QN][128] slab and two counters per CTA
+  const float* zero16;             // 16 bytes of zeros in global memory (stand-in for absent epilogue operands)
+  int coop;                        // 1: every CTA of a tile takes a share of the finish (needs a one-wave grid)
+  GemmEpi epi;
   int pre_p, pre_q;                // operand is a constant weight: its first pipeline stages load before pdl_wait()
   unsigned idesc_xor;              // debugging aid (SET_TC_IDESC_XOR)
   unsigned long long* trace;       // debugging aid: per-phase %globaltimer stamps of CTA 0 (SET_TC_TRACE)
@@ -80,7 +89,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // 3 converter saw P, 4 converter done, 5 MMA saw converted block, 6 MMA issued)
 #define KB_STAMP(i, slot)                                                                       \
   do {                                                                                          \
-    if (prm.trace && blockIdx.x == 0 && (i) < 48) prm.trace[400 + 8 * (i) + (slot)] = clock64(); \
+    if (prm.trace && blockIdx.x == 0 && (i) < 48) prm.trace[2100 + 8 * (i) + (slot)] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -260,7 +269,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
         const int s = j % NP;
         if (elect_one()) {
           mbar_expect_tx(p_full(s), Cfg::kPBytes);
-          tma_load_2d(base + s * Cfg::kPBytes, &prm.mapP[it.seg], p_full(s), it.kb * kBlockK, p0);
+          if (prm.nblk == 4) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              tma_load_2d(base + s * Cfg::kPBytes + g * 4096, &prm.mapP[it.seg], p_full(s), it.kb * kBlockK,
+                          g * prm.blk_stride + pt * 32);
+          } else {
+            tma_load_2d(base + s * Cfg::kPBytes, &prm.mapP[it.seg], p_full(s), it.kb * kBlockK, p0);
+          }
           KB_STAMP(j, 1);
         }
         __syncwarp();
@@ -397,13 +413,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
     // along the contiguous global direction: 128-bit global loads/stores/reductions, several rows in
     // flight per thread, no serial latency chain.
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const bool stager = (warp - 2) < 4;         // one warp per quarter moves TMEM -> smem
+    const int stage_grp = (warp - 2) >> 2;     // the warps sharing a quarter split the column blocks
     constexpr int EPW_N = QN + 4;              // staged row pitch, non-swap: [128 p][QN q]
     constexpr int EPW_S = kTileP + 4;          // staged row pitch, swap:     [QN q][128 p]
     float* ep = reinterpret_cast<float*>(gen_base);
     const int prow = quarter * 32 + lane;      // tile row held by this thread
 #pragma unroll 1
-    for (int cb = 0; stager && cb < QN / 32; ++cb) {
+    for (int cb = stage_grp; cb < QN / 32; cb += kConvGroups) {
       uint32_t r[32];
       if (nkb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), r);
@@ -424,6 +440,193 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");   // converter/epilogue warps only
     if (ct == 0) TC_STAMP(6);
+    if (prm.fused) {
+      // ---------------- fused epilogue (swap mode: staged tile = ep[q][p], q batch rows, p weight rows)
+      // Split-K partials go to per-CTA scratch slabs (plain vector stores; no atomics on C, no pre-zeroed C).
+      // Cooperative finish (grid fits one wave, so all partners are resident): every CTA of the tile waits for
+      // its partners and finishes 1/split of the tile's items; otherwise the last CTA to arrive finishes all.
+      // An item gathers every partial + bias/add/C operand it needs with independent 128-bit loads issued
+      // together (one L2 round trip), applies the cell, and stores.  Summation order is fixed (split 0, 1, ..).
+      __shared__ int s_last;
+      constexpr int kSlab = QN * kTileP;
+      const int rows = prm.Qr < QN ? prm.Qr : QN;
+      const int split = prm.split_k;
+      int nfin = 1, fin = 0;
+      bool finisher = true;
+      int* cnt = prm.counters + 2 * (blockIdx.x - ks);
+      if (split > 1) {
+        float* part = prm.scratch + (size_t)blockIdx.x * kSlab;
+        for (int e = ct; e < rows * 32; e += kCT) {
+          const int q = e >> 5, p4 = (e & 31) * 4;
+          __stcg(reinterpret_cast<float4*>(part + q * kTileP + p4), *reinterpret_cast<const float4*>(&ep[q * EPW_S + p4]));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");
+        if (ct == 0) TC_STAMP(9);
+        if (ct == 0) {
+          const int old = atomicAdd(cnt, 1);
+          if (prm.coop) {
+            int seen = old + 1;
+            while (seen < split) {
+              __nanosleep(40);
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+            }
+            s_last = 1;
+          } else {
+            const int last = (old == split - 1) ? 1 : 0;
+            if (last) *cnt = 0;   // every partner has arrived; the next launch finds the counter at zero
+            s_last = last;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");
+        finisher = (s_last != 0);
+        if (prm.coop) { nfin = split; fin = ks; }
+        if (ct == 0) TC_STAMP(10);
+        __threadfence();
+        if (ct == 0) TC_STAMP(11);
+      }
+      if (finisher) {
+        const GemmEpi& eo = prm.epi;
+        const float* pbase = prm.scratch + (size_t)(blockIdx.x - ks) * kSlab;
+        auto add4 = [](float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; };
+        // Absent operands read a 16-byte zero block instead of branching: an item's loads then form one
+        // straight-line batch the compiler issues back to back (one L2 round trip, not one per operand).
+        const float* zero4 = prm.zero16;
+        const int addq_mod = prm.add_mod > 0 ? prm.add_mod : (1 << 30);
+        struct Pre { float4 v[kMaxFusedSplit]; float4 b1, b2, ad, old; };
+        // request the pre-activation of 4 consecutive tile rows p4.. of batch row q (global column n..n+3)
+        auto request = [&](Pre& r, int q, int p4, int n) {
+          const float* src = pbase + q * kTileP + p4;
+#pragma unroll
+          for (int k2 = 0; k2 < kMaxFusedSplit; ++k2)
+            r.v[k2] = __ldcg(reinterpret_cast<const float4*>(k2 < split ? src + (size_t)k2 * kSlab : zero4));
+          r.b1 = __ldg(reinterpret_cast<const float4*>(prm.bias ? prm.bias + n : zero4));
+          r.b2 = __ldg(reinterpret_cast<const float4*>(prm.bias2 ? prm.bias2 + n : zero4));
+          r.ad = *reinterpret_cast<const float4*>(prm.add ? prm.add + (long)(q % addq_mod) * prm.ldadd + n : zero4);
+          r.old = *reinterpret_cast<const float4*>(prm.beta ? prm.C + (long)q * prm.ldc + n : zero4);
+        };
+        auto resolve = [&](const Pre& r, int q, int p4) -> float4 {
+          float4 acc;
+          if (split > 1) {
+            acc = r.v[0];
+#pragma unroll
+            for (int k2 = 1; k2 < kMaxFusedSplit; ++k2) add4(acc, r.v[k2]);   // absent splits contribute exact zeros
+          } else {
+            acc = *reinterpret_cast<const float4*>(&ep[q * EPW_S + p4]);
+          }
+          add4(acc, r.b1); add4(acc, r.b2); add4(acc, r.ad); add4(acc, r.old);
+          return acc;
+        };
+        if (eo.op == kEpiNone || eo.op == kEpiCopy2) {
+          const int items = rows * 32;   // (q, 4 consecutive rows of the tile)
+          const int i0 = (int)((long)items * fin / nfin), i1 = (int)((long)items * (fin + 1) / nfin);
+          const int D = eo.D;
+          for (int it = i0 + ct; it < i1; it += kCT) {
+            const int q = it >> 5, p4 = (it & 31) * 4;
+            const int n = pt * kTileP + p4;
+            if (n >= prm.Pr) continue;
+            Pre pr;
+            request(pr, q, p4, n);
+            const long x = (long)q * D + n;
+            float4 sel, cn, og;
+            if (eo.op == kEpiCopy2) {
+              sel = *reinterpret_cast<const float4*>(eo.sel + x);
+              cn = *reinterpret_cast<const float4*>(eo.cnew + x);
+              og = *reinterpret_cast<const float4*>(eo.gates + (long)q * eo.ld_gates + 3 * D + n);
+            }
+            const float4 v = resolve(pr, q, p4);
+            if (eo.op == kEpiNone) {
+              *reinterpret_cast<float4*>(prm.C + (long)q * prm.ldc + n) = v;
+            } else {
+              // copy gate (editnet.py:281-285): k = sigmoid(pre); c2 = k sel + (1-k) c_new; h2 = o tanh(c2)
+              float4 k, c, h;
+              k.x = sigmoidf_(v.x); k.y = sigmoidf_(v.y); k.z = sigmoidf_(v.z); k.w = sigmoidf_(v.w);
+              c.x = k.x * sel.x + (1.f - k.x) * cn.x; c.y = k.y * sel.y + (1.f - k.y) * cn.y;
+              c.z = k.z * sel.z + (1.f - k.z) * cn.z; c.w = k.w * sel.w + (1.f - k.w) * cn.w;
+              h.x = og.x * tanhf(c.x); h.y = og.y * tanhf(c.y); h.z = og.z * tanhf(c.z); h.w = og.w * tanhf(c.w);
+              *reinterpret_cast<float4*>(eo.kgate + x) = k;
+              *reinterpret_cast<float4*>(eo.c_out + x) = c;
+              *reinterpret_cast<float4*>(eo.h_out + (long)q * eo.ld_h + n) = h;
+              if (eo.h2drop) {
+                float4 hd = h;
+                if (eo.train) {
+                  const uint32_t keep = drop_keep4(eo.seed, kSiteFc, (uint64_t)(eo.drop_base + x));
+                  hd.x = (keep & 1u) ? h.x * 2.f : 0.f; hd.y = (keep & 2u) ? h.y * 2.f : 0.f;
+                  hd.z = (keep & 4u) ? h.z * 2.f : 0.f; hd.w = (keep & 8u) ? h.w * 2.f : 0.f;
+                }
+                *reinterpret_cast<float4*>(eo.h2drop + x) = hd;
+              }
+            }
+          }
+        } else {
+          // 4-gate cells; tile rows: [i | f | g | o] x 32 units (editnet.py:233-244 LSTMCellC / nn.LSTMCell;
+          // :272-279 copy-LSTM stage 1).  Item = (q, 2 consecutive units): with the usual 4-way split that is one
+          // item per epilogue thread -- the cell's ~20 transcendentals are latency-bound per thread, so the work is
+          // spread as thin as the thread count allows.
+          const int items = rows * 16;
+          const int i0 = (int)((long)items * fin / nfin), i1 = (int)((long)items * (fin + 1) / nfin);
+          const int D = eo.D;
+          auto ld2 = [](const float* ptr) { return __ldcg(reinterpret_cast<const float2*>(ptr)); };
+          for (int it = i0 + ct; it < i1; it += kCT) {
+            const int q = it >> 4, u0 = (it & 15) * 2;
+            const int unit = pt * 32 + u0;
+            if (unit >= D) continue;
+            float2 v[4][kMaxFusedSplit], b1[4], b2[4], ad[4], old[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = g * D + unit;
+              const float* src = pbase + q * kTileP + g * 32 + u0;
+#pragma unroll
+              for (int k2 = 0; k2 < kMaxFusedSplit; ++k2) v[g][k2] = ld2(k2 < split ? src + (size_t)k2 * kSlab : zero4);
+              b1[g] = ld2(prm.bias ? prm.bias + n : zero4);
+              b2[g] = ld2(prm.bias2 ? prm.bias2 + n : zero4);
+              ad[g] = ld2(prm.add ? prm.add + (long)(q % addq_mod) * prm.ldadd + n : zero4);
+              old[g] = ld2(prm.beta ? prm.C + (long)q * prm.ldc + n : zero4);
+            }
+            const float2 cp = ld2(eo.c_prev + (long)q * D + unit);
+            float2 pre[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float2 acc;
+              if (split > 1) {
+                acc = v[g][0];
+#pragma unroll
+                for (int k2 = 1; k2 < kMaxFusedSplit; ++k2) { acc.x += v[g][k2].x; acc.y += v[g][k2].y; }
+              } else {
+                acc = *reinterpret_cast<const float2*>(&ep[q * EPW_S + g * 32 + u0]);
+              }
+              acc.x += b1[g].x; acc.y += b1[g].y; acc.x += b2[g].x; acc.y += b2[g].y;
+              acc.x += ad[g].x; acc.y += ad[g].y; acc.x += old[g].x; acc.y += old[g].y;
+              pre[g] = acc;
+            }
+            float2 gi, gf, gg, go, c;
+            gi.x = sigmoidf_(pre[0].x); gi.y = sigmoidf_(pre[0].y);
+            gf.x = sigmoidf_(pre[1].x); gf.y = sigmoidf_(pre[1].y);
+            gg.x = tanhf(pre[2].x); gg.y = tanhf(pre[2].y);
+            go.x = sigmoidf_(pre[3].x); go.y = sigmoidf_(pre[3].y);
+            c.x = gf.x * cp.x + gi.x * gg.x; c.y = gf.y * cp.y + gi.y * gg.y;
+            float* g = eo.gates + (long)q * eo.ld_gates + unit;
+            *reinterpret_cast<float2*>(g) = gi; *reinterpret_cast<float2*>(g + D) = gf;
+            *reinterpret_cast<float2*>(g + 2 * D) = gg; *reinterpret_cast<float2*>(g + 3 * D) = go;
+            *reinterpret_cast<float2*>(eo.c_out + (long)q * D + unit) = c;
+            if (eo.op == kEpiLstm) {
+              float2 h;
+              h.x = go.x * tanhf(c.x); h.y = go.y * tanhf(c.y);
+              *reinterpret_cast<float2*>(eo.h_out + (long)q * eo.ld_h + unit) = h;
+            }
+          }
+        }
+      }
+      if (ct == 0) TC_STAMP(12);
+      if (split > 1 && prm.coop) {
+        // the last CTA to finish reading the slabs re-arms both counters for the next launch
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");
+        if (ct == 0) {
+          const int old = atomicAdd(cnt + 1, 1);
+          if (old == split - 1) { cnt[0] = 0; cnt[1] = 0; }
+        }
+      }
+    } else {
     const bool lead = (ks == 0);               // split 0 carries bias / addend
     const bool atomic = prm.split_k > 1;
     const int width = prm.swap ? kTileP : QN;  // contiguous extent of a staged row
@@ -475,6 +678,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
         for (int k = 0; k < nv; ++k) cp[k] = prm.beta ? cp[k] + v[k] : v[k];
       }
     }
+    }   // !fused
   }
   if (threadIdx.x == 64) TC_STAMP(7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -492,6 +696,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 bool g_tc_ready = false, g_tc_failed = false;
+// split-K scratch of the fused epilogue: one [128][128] fp32 slab and one arrival counter per CTA of a launch.
+// Launches are stream-ordered (a launch's epilogue begins after its grid dependency resolved), so one slab set
+// serves every launch of the calling stream; the library is used from one stream at a time.
+constexpr int kScratchSlots = 320;
+int g_sm_count = 0;
+float* g_tc_scratch = nullptr;
+int* g_tc_counters = nullptr;
 std::once_flag g_tc_once;
 
 void tc_init() {
@@ -510,6 +721,15 @@ void tc_init() {
   set_attr(gemm_tc_kernel<64, 2>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 2>, TcCfg<128>::kSmemBytes);
   set_attr(gemm_tc_kernel<64, 5>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 5>, TcCfg<128>::kSmemBytes);
   set_attr(gemm_tc_kernel<64, 8>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8>, TcCfg<128>::kSmemBytes);
+  ok = ok && cudaMalloc(&g_tc_scratch, sizeof(float) * (size_t)kScratchSlots * kTileP * 128) == cudaSuccess;
+  // (+ 16 bytes of zeros behind the counters: TcParams::zero16)
+  ok = ok && cudaMalloc(&g_tc_counters, sizeof(int) * (2 * kScratchSlots + 4)) == cudaSuccess;
+  ok = ok && cudaMemset(g_tc_counters, 0, sizeof(int) * (2 * kScratchSlots + 4)) == cudaSuccess;
+  {
+    int dev = 0;
+    ok = ok && cudaGetDevice(&dev) == cudaSuccess &&
+         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+  }
   if (!ok) {
     cudaGetLastError();
     g_tc_failed = true;
@@ -558,12 +778,29 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   if (swap && (g.c_inner > 0)) return false;
   prm.swap = swap; prm.Pr = Pr; prm.Qr = Qr;
   prm.nseg = g.nseg;
+  // fused epilogue (scratch-slab split-K + optional cell): swap mode, plain row-major C, 16-byte aligned vectors
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  static const int fuse_on = getenv("SET_TC_FUSE") ? atoi(getenv("SET_TC_FUSE")) : 1;
+  const bool fuse_ok = fuse_on && swap && g.act == 0 && g.c_inner == 0 && !g.c_row_len && g.N % 4 == 0 && al16(g.C) &&
+                       g.ldc % 4 == 0 && al16(g.bias) && al16(g.bias2) && al16(g.add) && g.ldadd % 4 == 0;
+  const int op = fuse_ok ? g.epi.op : kEpiNone;
+  const bool gates4 = (op == kEpiLstm || op == kEpiCopy1);
+  if (gates4 && !(g.epi.D % 32 == 0 && g.N == 4 * g.epi.D)) return false;
+  if (op == kEpiCopy2 && g.N != g.epi.D) return false;
+  // Plain split-K keeps the fire-and-forget red.global.add epilogue (measured faster than the slab protocol
+  // when there is no cell to apply); the slab path is for problems that carry a cell.
+  prm.fused = (fuse_ok && op != kEpiNone) ? 1 : 0;
+  prm.nblk = gates4 ? 4 : 1;
+  prm.blk_stride = gates4 ? g.epi.D : 0;
+  prm.epi = g.epi; prm.epi.op = op;
+  prm.scratch = g_tc_scratch; prm.counters = g_tc_counters;
+  prm.zero16 = reinterpret_cast<const float*>(g_tc_counters + 2 * kScratchSlots);
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
     prm.K[s] = sg.K;
     const float* Pp = swap ? sg.B : sg.A; const long Pld = swap ? sg.ldb : sg.lda;
     const float* Qp = swap ? sg.A : sg.B; const long Qld = swap ? sg.lda : sg.ldb;
-    if (!make_map(&prm.mapP[s], Pp, Pr, sg.K, Pld, kBlockK, kTileP)) return false;
+    if (!make_map(&prm.mapP[s], Pp, Pr, sg.K, Pld, kBlockK, kTileP / prm.nblk)) return false;
     if (!make_map(&prm.mapQ[s], Qp, Qr, sg.K, Qld, kBlockK, QN)) return false;
   }
   prm.tiles_p = (Pr + kTileP - 1) / kTileP;
@@ -607,32 +844,65 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     ++grp.n;
   }
   if (grp.n == 0) return SET_OK;
-  // split-K: spread the group over ~all SMs (partials meet in global reductions)
+  // split-K: spread the group over one wave of the 148 SMs (a second wave would repeat every CTA's fixed
+  // prologue/epilogue).  Greedy balance: the next split goes to the problem whose CTAs carry the most K-blocks.
+  long nkbs[8]; int tiles[8], splits[8]; bool splittable[8];
+  static const int max_fused_split = []{
+    int v = getenv("SET_TC_MAX_FSPLIT") ? atoi(getenv("SET_TC_MAX_FSPLIT")) : 6;
+    return v < 1 ? 1 : (v > kMaxFusedSplit ? kMaxFusedSplit : v);
+  }();
+  for (int k = 0; k < grp.n; ++k) {
+    const GemmProblem& g = probs[idx[k]];
+    nkbs[k] = 0;
+    for (int s = 0; s < g.nseg; ++s) nkbs[k] += (g.seg[s].K + kBlockK - 1) / kBlockK;
+    tiles[k] = grp.p[k].tiles_p * grp.p[k].tiles_q;
+    splits[k] = 1;
+    splittable[k] = (g.act == 0 && !(g.c_inner > 0 || g.c_row_len));
+  }
+  if (tiles_total < 148) {
+    long ctas = tiles_total;
+    for (;;) {
+      int best = -1; double best_load = 0.0;
+      for (int k = 0; k < grp.n; ++k) {
+        if (!splittable[k] || ctas + tiles[k] > 148) continue;
+        const int cap = grp.p[k].fused ? max_fused_split : 16;
+        if (splits[k] >= cap || nkbs[k] / (splits[k] + 1) < 4) continue;
+        const double load = (double)nkbs[k] / splits[k];
+        if (load > best_load) { best_load = load; best = k; }
+      }
+      if (best < 0) break;
+      ++splits[best];
+      ctas += tiles[best];
+    }
+    // a single long-K problem that fills only ~half the machine: three partials over two waves is ~1.5x faster
+    if (grp.n == 1 && splits[0] == 1 && splittable[0] && tiles_total * 3 <= 2 * 148 && nkbs[0] >= 96) splits[0] = 3;
+  }
   int cta = 0;
   for (int k = 0; k < grp.n; ++k) {
     TcParams& prm = grp.p[k];
     const GemmProblem& g = probs[idx[k]];
-    long nkb = 0;
-    for (int s = 0; s < g.nseg; ++s) nkb += (g.seg[s].K + kBlockK - 1) / kBlockK;
-    int split = 1;
-    if (g.act == 0 && tiles_total < 148 && !(g.c_inner > 0 || g.c_row_len)) {
-      // fill one wave of the 148 SMs (a second wave would repeat every CTA's fixed prologue/epilogue)
-      split = (int)(148 / tiles_total);
-      const int max_split = (int)(nkb / 4 > 0 ? nkb / 4 : 1);
-      if (split > max_split) split = max_split;
-      if (split > 16) split = 16;
-      if (split < 1) split = 1;
-      // a long-K problem that fills only ~half the machine: three partials over two waves is ~1.5x faster
-      if (split == 1 && tiles_total * 3 <= 2 * 148 && nkb >= 96) split = 3;
-    }
+    const int split = splits[k];
     prm.split_k = split;
-    if (split > 1 && !g.beta && !g.c_zeroed)   // partial sums are reduced into C: it must start at zero
+    if (prm.fused && split == 1 && prm.epi.op == kEpiNone) prm.fused = 0;   // nothing to reduce, nothing to apply
+    if (prm.fused && cta + tiles[k] * split > kScratchSlots) {
+      // (cannot happen with the one-wave heuristic above; guard the slab indexing anyway)
+      set_record_error("fused GEMM launch exceeds the split-K scratch");
+      return SET_ERR_ARG;
+    }
+    if (!prm.fused && split > 1 && !g.beta && !g.c_zeroed)   // partial sums are reduced into C: it must start at zero
       SET_CHECK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, stream));
+    if (prm.fused && prm.epi.op != kEpiNone && g.epi_done) *g.epi_done = 1;
     grp.cta_start[k] = cta;
-    cta += prm.tiles_p * prm.tiles_q * split;
+    cta += tiles[k] * split;
     taken[idx[k]] = true;
   }
   grp.cta_start[grp.n] = cta;
+  {
+    // cooperative finish spins on partner CTAs: only when the whole grid is resident at once (one CTA per SM)
+    static const int coop_on = getenv("SET_TC_COOP") ? atoi(getenv("SET_TC_COOP")) : 1;
+    const int coop = (coop_on && cta <= g_sm_count) ? 1 : 0;
+    for (int k = 0; k < grp.n; ++k) grp.p[k].coop = coop;
+  }
   if (g_tc_trace && g_tc_trace_stride > 0) {
     if (g_tc_trace_left > 0) {
       // header: [8] grid size, [9] problems in the group, [10] K-blocks per CTA of problem 0

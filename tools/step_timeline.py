@@ -26,7 +26,7 @@ args = [b[k].to(dev) for k in ("feats", "caps", "caplens", "prev", "prev_len")]
 for _ in range(3):
     tr.step(*args)
 torch.cuda.synchronize()
-STRIDE = 16 + 2 * 1024
+STRIDE = 2100 + 8 * 48 + 16
 N = first + count
 buf = torch.zeros(N * STRIDE, dtype=torch.int64, device=dev)
 lib.set_gemm_trace_seq(L.ptr(buf), STRIDE, N)
@@ -36,13 +36,13 @@ lib.set_gemm_trace(None)
 t = buf.cpu().view(N, STRIDE)
 rows = []
 for n in range(N):
-    st = t[n, 16::2].double()
-    en = t[n, 17::2].double()
+    st = t[n, 16:2016:2].double()
+    en = t[n, 17:2017:2].double()
     ok = st > 0
     if not bool(ok.any()):
         continue
     rows.append(dict(n=n, ctas=int(ok.sum()), s_first=float(st[ok].min()), s_last=float(st[ok].max()),
-                     e_first=float(en[ok].min()), e_last=float(en[ok].max()), stamps=[float(x) for x in t[n, :9]]))
+                     e_first=float(en[ok].min()), e_last=float(en[ok].max()), stamps=[float(x) for x in t[n, :16]]))
 if not rows:
     print("no traced launches")
     sys.exit(0)
@@ -58,11 +58,14 @@ for i, r in enumerate(rows):
     print("%5d %4d | %9.1f %7.1f | %12.1f %9.1f %9.1f | %8.1f %8.1f | %5.1f %6.1f   (next starts +%.1f)" % (
         r["n"], r["ctas"], (r["s_first"] - t0) / 1e3, rel(r["s_last"]), rel(sp[2]), rel(sp[4]), rel(sp[7]),
         rel(r["e_first"]), rel(r["e_last"]), (r["e_last"] - r["s_first"]) / 1e3, gap, nxt_overlap))
+    if os.environ.get("EPI"):
+        print("        cta0 epilogue: loop-done %.1f accum %.1f staged %.1f partial-written %.1f partners-in %.1f fenced %.1f finished %.1f exit %.1f" % tuple(
+            rel(sp[k]) for k in (4, 5, 6, 9, 10, 11, 12, 8)))
 
 # per-K-block SM-clock stamps of CTA 0 for selected launches (KB_STAMP in gemm_tc.cu)
 names = ["Q issued", "P issued", "conv saw Q", "conv saw P", "conv done", "mma saw", "mma issued"]
 for n in [int(x) for x in os.environ.get("KB_LAUNCHES", "").split(",") if x]:
-    kb = t[n, 400:400 + 8 * 48].view(48, 8)
+    kb = t[n, 2100:2100 + 8 * 48].view(48, 8)
     c0 = int(kb[kb > 0].min()) if bool((kb > 0).any()) else 0
     print("launch %d: per-K-block stamps of CTA 0 (SM cycles since the first stamp)" % n)
     print("  kb | " + " | ".join("%10s" % x for x in names))
