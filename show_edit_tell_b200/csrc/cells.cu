@@ -9,7 +9,8 @@ namespace set {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kAttnThreads = 1024;   // one CTA per (sample, attention): latency-bound, so many warps
+constexpr int kAttnThreads = 512;    // CTAs are latency-bound: many warps, and several CTAs per sample (see kVisSlices)
+constexpr int kVisSlices = 4;        // column slices of the region-feature context / unit slices of the score MLP
 
 inline int blocks_for(long n, int per_block) {
   long b = (n + per_block - 1) / per_block;
@@ -315,7 +316,10 @@ __global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restr
 }
 
 // ------------------------------------------------------------------------ attention
-// dynamic smem: a2[A] | wv[A] | sc[max(P,R)] | red[40]
+// grid (b, 1 + slices): y == 0 caption attention + select; y >= 1 visual attention, each CTA recomputes the R
+// scores (36 x 512: cheap) and reduces one column slice of the 36 x 2048 region features, so the 295 KB per
+// sample are pulled through `slices` SMs instead of one.
+// dynamic smem: a2[A] | wv[A] | sc[max(P,R)] | red[40] | part[4 * blockDim]
 __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnFwdArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -364,7 +368,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnF
   }
   __syncthreads();
   float* alpha_out = cap ? a.alpha_c + (long)i * a.P : a.alpha_v + (long)i * a.R;
-  for (int j = tid; j < n; j += blockDim.x) alpha_out[j] = sc[j];
+  if (blockIdx.y <= 1)
+    for (int j = tid; j < n; j += blockDim.x) alpha_out[j] = sc[j];
   if (cap) {
     const float* ph = a.prev_h + (long)i * a.P * a.D;
     for (int d = tid; d < a.D; d += blockDim.x) {
@@ -385,54 +390,64 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnF
     const float* ft = a.feats + (long)i * a.R * a.F;
     float* out = a.att_img + (long)i * a.ld_img;
     const int F4 = a.F >> 2;
-    for (int f4 = tid; f4 < F4; f4 += blockDim.x) {
+    const int slices = gridDim.y - 1, vs = blockIdx.y - 1;
+    const int per = (F4 + slices - 1) / slices;
+    const int c0 = vs * per, c1 = min(F4, c0 + per);
+    // threads = (column, row group): the regions of a column are split over G groups whose partial sums meet
+    // in shared memory, so every thread keeps ~R/G independent 128-bit loads in flight
+    float4* part = reinterpret_cast<float4*>(sm + 2 * A + ((n + 3) & ~3) + 40);
+    const int cw = min(per, (int)blockDim.x);
+    const int G = blockDim.x / cw;
+    const int g = tid / cw, c = tid % cw;
+    for (int cb = c0; cb < c1; cb += cw) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
-      for (int r = 0; r < nvalid; ++r) {
-        const float al = sc[r];
-        const float4 v = __ldg(reinterpret_cast<const float4*>(ft + (long)r * a.F) + f4);
-        acc.x += al * v.x; acc.y += al * v.y; acc.z += al * v.z; acc.w += al * v.w;
+      const int col = cb + c;
+      if (g < G && col < c1) {
+#pragma unroll 9
+        for (int r = g; r < nvalid; r += G) {
+          const float al = sc[r];
+          const float4 v = __ldg(reinterpret_cast<const float4*>(ft + (long)r * a.F) + col);
+          acc.x += al * v.x; acc.y += al * v.y; acc.z += al * v.z; acc.w += al * v.w;
+        }
       }
-      reinterpret_cast<float4*>(out)[f4] = acc;
+      part[tid] = acc;
+      __syncthreads();
+      if (g == 0 && col < c1) {
+        for (int k = 1; k < G; ++k) {
+          const float4 v = part[k * cw + c];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[col] = acc;
+      }
+      __syncthreads();
     }
   }
 }
 
-// dynamic smem: a2[A] | wv[A] | al[n] | dal[n] | ds[n] | red[40]
-__global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnBwdArgs a) {
+// Attention backward runs as two chained kernels so that no CTA has to pull a whole sample through one SM:
+//   (1) attention_bwd_dal_kernel: d alpha_j = <d context, value_j> (+ select term); grid (b, 1 + slices), the
+//       visual rows are dealt round-robin to `slices` CTAs; results go to a small global scratch;
+//   (2) attention_bwd_main_kernel: softmax backward (recomputed by every CTA of the sample: n <= 100 values),
+//       then y == 0: value gradients of the caption attention (d prev_h, d prev_m);
+//            y in [1, 1+cs): unit slices of the caption score MLP;  y >= 1+cs: unit slices of the visual score MLP.
+__global__ void __launch_bounds__(kAttnThreads) attention_bwd_dal_kernel(const AttnBwdArgs a, float* __restrict__ dal_out) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];
-  const int A = a.A;
   const bool cap = (blockIdx.y == 0);
   if (cap && a.att1c == nullptr) return;
   if (!cap && a.att1v == nullptr) return;
-  const int n = cap ? a.P : a.R;
-  float* a2 = sm;
-  float* wv = sm + A;
-  float* al = sm + 2 * A;
-  float* dal = al + n;
-  float* ds = dal + n;
-  float* red = ds + n;
   const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const float* s2row = a.s2 + (long)i * a.ld_s2 + (cap ? 0 : A);
-  const float* w = cap ? a.cap_w : a.vis_w;
-  const float* alpha = cap ? a.alpha_c + (long)i * a.P : a.alpha_v + (long)i * a.R;
-  for (int x = tid; x < A; x += blockDim.x) { a2[x] = s2row[x]; wv[x] = w[x]; }
-  for (int j = tid; j < n; j += blockDim.x) al[j] = alpha[j];
-  __syncthreads();
-  const int nvalid = cap ? n : (a.nreg ? a.nreg[i] : n);
-  const int js = (cap && a.dsel) ? a.sel_idx[i] : -1;
-  // d alpha_j = <dcontext, value_j> (+ select term)
+  float* dal = dal_out + (long)i * (a.P + a.R);
   if (cap) {
+    const int js = a.dsel ? a.sel_idx[i] : -1;
     const float* ph = a.prev_h + (long)i * a.P * a.D;
     const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
-    for (int j = wid; j < n; j += nw) {
+    for (int j = wid; j < a.P; j += nw) {
       float s = 0.f;
       {
         const float4* x4 = reinterpret_cast<const float4*>(dc);
         const float4* y4 = reinterpret_cast<const float4*>(ph + (long)j * a.D);
-#pragma unroll 4
+#pragma unroll 8
         for (int d = lane; d < a.D / 4; d += 32) {
           const float4 x = x4[d], y = __ldg(y4 + d);
           s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
@@ -441,7 +456,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
       if (j == js) {
         const float4* y4 = reinterpret_cast<const float4*>(a.prev_m + ((long)i * a.P + j) * a.D);
         const float4* x4 = reinterpret_cast<const float4*>(a.dsel + (long)i * a.D);
-#pragma unroll 4
+#pragma unroll 8
         for (int d = lane; d < a.D / 4; d += 32) {
           const float4 x = x4[d], y = __ldg(y4 + d);
           s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
@@ -451,28 +466,59 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
       if (lane == 0) dal[j] = s;
     }
   } else {
+    const int slices = gridDim.y - 1, vs = blockIdx.y - 1;
+    const int nvalid = a.nreg ? a.nreg[i] : a.R;
     const float* ft = a.feats + (long)i * a.R * a.F;
     const float* di = a.datt_img + (long)i * a.ld_dimg;
-    for (int r = wid; r < n; r += nw) {
+    for (int r = vs + slices * wid; r < a.R; r += slices * nw) {
       float s = 0.f;
       if (r < nvalid) {
         const float4* x4 = reinterpret_cast<const float4*>(di);
         const float4* y4 = reinterpret_cast<const float4*>(ft + (long)r * a.F);
-#pragma unroll 4
+#pragma unroll 8
         for (int f = lane; f < a.F / 4; f += 32) {
           const float4 x = x4[f], y = __ldg(y4 + f);
           s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
         }
       }
       s = warp_sum(s);
-      if (lane == 0) dal[r] = s;
+      if (lane == 0) dal[a.P + r] = s;
     }
   }
+}
+
+// dynamic smem: a2[A] | wv[A] | al[n] | ds[n] | red[40] | part[2 * blockDim]
+__global__ void __launch_bounds__(kAttnThreads) attention_bwd_main_kernel(const AttnBwdArgs a, const float* __restrict__ dal_in,
+                                                                          int cap_slices) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int A = a.A;
+  const int y = blockIdx.y;
+  const bool cap = (y < 1 + cap_slices);
+  if (cap && a.att1c == nullptr) return;
+  if (!cap && a.att1v == nullptr) return;
+  const int n = cap ? a.P : a.R;
+  const int npad = (n + 3) & ~3;
+  float* a2 = sm;
+  float* wv = sm + A;
+  float* al = sm + 2 * A;
+  float* ds = al + npad;
+  float* red = ds + npad;
+  float* part = red + 40;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const float* s2row = a.s2 + (long)i * a.ld_s2 + (cap ? 0 : A);
+  const float* w = cap ? a.cap_w : a.vis_w;
+  const float* alpha = cap ? a.alpha_c + (long)i * a.P : a.alpha_v + (long)i * a.R;
+  const float* dal = dal_in + (long)i * (a.P + a.R) + (cap ? 0 : a.P);
+  for (int x = tid; x < A; x += blockDim.x) { a2[x] = s2row[x]; wv[x] = w[x]; }
+  for (int j = tid; j < n; j += blockDim.x) al[j] = alpha[j];
   __syncthreads();
+  const int nvalid = cap ? n : (a.nreg ? a.nreg[i] : n);
   // softmax backward
-  float part = 0.f;
-  for (int j = tid; j < n; j += blockDim.x) part += al[j] * dal[j];
-  const float dot = block_sum(part, red);
+  float p = 0.f;
+  for (int j = tid; j < n; j += blockDim.x) p += al[j] * dal[j];
+  const float dot = block_sum(p, red);
   float dsum = 0.f;
   for (int j = tid; j < n; j += blockDim.x) {
     float v = al[j] * (dal[j] - dot);
@@ -482,15 +528,21 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
     dsum += v;
   }
   const float dbias = block_sum(dsum, red);  // also orders ds[] writes before the reads below
-  if (tid == 0) atomicAdd(cap ? a.dcap_b : a.dvis_b, dbias);
-  // value gradients
-  if (cap) {
+  if (y == 0) {
+    // value gradients of the caption attention (+ the bias gradient, once per sample)
+    if (tid == 0) atomicAdd(a.dcap_b, dbias);
+    const int js = a.dsel ? a.sel_idx[i] : -1;
     const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
     float* dph = a.dprev_h + (long)i * a.P * a.D;
-    for (int d = tid; d < a.D; d += blockDim.x) {
-      const float g = dc[d];
-#pragma unroll 6
-      for (int j = 0; j < n; ++j) dph[(long)j * a.D + d] += al[j] * g;
+    const int D4 = a.D >> 2;
+    for (int e = tid; e < n * D4; e += blockDim.x) {
+      const int j = e / D4, d4 = e % D4;
+      const float4 g = reinterpret_cast<const float4*>(dc)[d4];
+      float4* dst = reinterpret_cast<float4*>(dph + (long)j * a.D) + d4;
+      float4 v = *dst;
+      const float aj = al[j];
+      v.x += aj * g.x; v.y += aj * g.y; v.z += aj * g.z; v.w += aj * g.w;
+      *dst = v;
     }
     if (js >= 0) {
       const float best = al[js];
@@ -499,28 +551,46 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_kernel(const AttnB
       const float* dsl = a.dsel + (long)i * a.D;
       for (int d = tid; d < a.D; d += blockDim.x) dpm[d] += wsel * dsl[d];
     }
+    return;
   }
-  // score-MLP backward: thread per attention unit
+  // score-MLP backward for a slice of the attention units: threads = (unit, row group)
+  const int slices = cap ? cap_slices : (int)gridDim.y - 1 - cap_slices;
+  const int sl = cap ? y - 1 : y - 1 - cap_slices;
+  if (!cap && sl == 0 && tid == 0) atomicAdd(a.dvis_b, dbias);
+  const int per = (A + slices - 1) / slices;
+  const int x0 = sl * per, x1 = min(A, x0 + per);
   const float* att1 = cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A;
   float* datt1 = cap ? a.datt1c + (long)i * a.P * A : a.datt1v + (long)i * a.R * A;
   const bool accum = cap ? true : (a.datt1v_accum != 0);
   float* ds2row = a.ds2 + (long)i * a.ld_ds2 + (cap ? 0 : A);
   float* dwv = cap ? a.dcap_w : a.dvis_w;
-  for (int x = tid; x < A; x += blockDim.x) {
+  const int cw = min(per, (int)blockDim.x);
+  const int G = blockDim.x / cw;
+  const int g = tid / cw, c = tid % cw;
+  for (int xb = x0; xb < x1; xb += cw) {
+    const int x = xb + c;
     float d2 = 0.f, dw = 0.f;
-    const float av = a2[x], wx = wv[x];
-#pragma unroll 6
-    for (int j = 0; j < n; ++j) {
-      const float pre = att1[(long)j * A + x] + av;
-      float y, dpre;
-      if (cap) { y = tanhf(pre); dpre = ds[j] * wx * (1.f - y * y); }
-      else { y = fmaxf(pre, 0.f); dpre = (pre > 0.f) ? ds[j] * wx : 0.f; }
-      dw += ds[j] * y;
-      d2 += dpre;
-      if (accum) datt1[(long)j * A + x] += dpre; else datt1[(long)j * A + x] = dpre;
+    if (g < G && x < x1) {
+      const float av = a2[x], wx = wv[x];
+#pragma unroll 4
+      for (int j = g; j < n; j += G) {
+        const float pre = att1[(long)j * A + x] + av;
+        float yv, dpre;
+        if (cap) { yv = tanhf(pre); dpre = ds[j] * wx * (1.f - yv * yv); }
+        else { yv = fmaxf(pre, 0.f); dpre = (pre > 0.f) ? ds[j] * wx : 0.f; }
+        dw += ds[j] * yv;
+        d2 += dpre;
+        if (accum) datt1[(long)j * A + x] += dpre; else datt1[(long)j * A + x] = dpre;
+      }
     }
-    ds2row[x] = d2;
-    atomicAdd(dwv + x, dw);
+    part[2 * tid] = d2; part[2 * tid + 1] = dw;
+    __syncthreads();
+    if (g == 0 && x < x1) {
+      for (int k = 1; k < G; ++k) { d2 += part[2 * (k * cw + c)]; dw += part[2 * (k * cw + c) + 1]; }
+      ds2row[x] = d2;
+      atomicAdd(dwv + x, dw);
+    }
+    __syncthreads();
   }
 }
 
@@ -692,7 +762,7 @@ static void init_carveout() {
   prefer_smem(vis_dropout_bwd_kernel); prefer_smem(relu_bwd_kernel); prefer_smem(tanh_bwd_kernel);
   prefer_smem(lstm_fwd_kernel); prefer_smem(lstm_bwd_kernel); prefer_smem(enc_lstm_bwd_kernel);
   prefer_smem(bilstm_fwd_kernel); prefer_smem(bilstm_bwd_kernel); prefer_smem(enc_mask_kernel);
-  prefer_smem(attention_fwd_kernel); prefer_smem(attention_bwd_kernel); prefer_smem(ctx_gate_fwd_kernel);
+  prefer_smem(attention_fwd_kernel); prefer_smem(attention_bwd_dal_kernel); prefer_smem(attention_bwd_main_kernel); prefer_smem(ctx_gate_fwd_kernel);
   prefer_smem(ctx_gate_bwd_kernel); prefer_smem(copy1_fwd_kernel); prefer_smem(copy2_fwd_kernel);
   prefer_smem(copy2_bwd_kernel); prefer_smem(copy1_bwd_kernel); prefer_smem(dropout_fwd_kernel);
   prefer_smem(transpose_kernel); prefer_smem(sum_time_kernel); prefer_smem(keep_mask_kernel);
@@ -804,17 +874,31 @@ int attention_fwd(const AttnFwdArgs& a, cudaStream_t s) {
   if (a.b <= 0) return SET_OK;
   SET_REQUIRE(a.F % 4 == 0, "F % 4");
   const int n = a.P > a.R ? a.P : a.R;
-  const size_t smem = sizeof(float) * (2 * a.A + n + 40);
+  const size_t smem = sizeof(float) * (2 * a.A + ((n + 3) & ~3) + 40 + 4 * kAttnThreads);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  SET_CHECK_CUDA(launch_chain(attention_fwd_kernel, dim3(dim3(a.b, 2)), dim3(kAttnThreads), smem, s, a));
+  SET_CHECK_CUDA(launch_chain(attention_fwd_kernel, dim3(a.b, 1 + (a.att1v ? kVisSlices : 0)), dim3(kAttnThreads), smem, s, a));
   LAUNCH_OK();
 }
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   if (a.b <= 0) return SET_OK;
   const int n = a.P > a.R ? a.P : a.R;
-  const size_t smem = sizeof(float) * (2 * a.A + 3 * n + 40);
+  const size_t smem = sizeof(float) * (2 * a.A + 2 * ((n + 3) & ~3) + 40 + 2 * kAttnThreads);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  SET_CHECK_CUDA(launch_chain(attention_bwd_kernel, dim3(dim3(a.b, 2)), dim3(kAttnThreads), smem, s, a));
+  // d alpha scratch between the two kernels (library-owned, grown on demand; single-stream use like the GEMM scratch)
+  static float* dal = nullptr;
+  static size_t dal_cap = 0;
+  const size_t need = (size_t)a.b * (a.P + a.R);
+  if (need > dal_cap) {
+    if (dal) SET_CHECK_CUDA(cudaFree(dal));
+    dal_cap = need < 65536 ? 65536 : 2 * need;
+    SET_CHECK_CUDA(cudaMalloc(&dal, sizeof(float) * dal_cap));
+  }
+  const int vis = a.att1v ? kVisSlices : 0;
+  const int cs = 2;   // unit slices of the caption score MLP
+  SET_CHECK_CUDA(launch_chain(attention_bwd_dal_kernel, dim3(a.b, 1 + vis), dim3(kAttnThreads), 0, s, a, dal));
+  set_count_launch(1);
+  SET_CHECK_CUDA(launch_chain(attention_bwd_main_kernel, dim3(a.b, 1 + cs + vis), dim3(kAttnThreads), smem, s, a,
+                              (const float*)dal, cs));
   LAUNCH_OK();
 }
 int ctx_gate_fwd(const float* s4, long ld_s4, const float* th, long ld_th, float* zst, float* att_cap,
