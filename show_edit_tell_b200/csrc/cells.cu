@@ -9,8 +9,9 @@ namespace set {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kAttnThreads = 512;    // CTAs are latency-bound: many warps, and several CTAs per sample (see kVisSlices)
+constexpr int kAttnThreads = 256;    // CTAs are latency-bound: many warps, and several CTAs per sample (see kVisSlices)
 constexpr int kVisSlices = 4;        // column slices of the region-feature context / unit slices of the score MLP
+constexpr int kCapSlices = 2;        // same for the caption attention
 
 inline int blocks_for(long n, int per_block) {
   long b = (n + per_block - 1) / per_block;
@@ -316,23 +317,118 @@ __global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restr
 }
 
 // ------------------------------------------------------------------------ attention
-// grid (b, 1 + slices): y == 0 caption attention + select; y >= 1 visual attention, each CTA recomputes the R
-// scores (36 x 512: cheap) and reduces one column slice of the 36 x 2048 region features, so the 295 KB per
-// sample are pulled through `slices` SMs instead of one.
-// dynamic smem: a2[A] | wv[A] | sc[max(P,R)] | red[40] | part[4 * blockDim]
-__global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnFwdArgs a) {
+// Every loop below is latency-bound (a sample's rows are HBM- or L2-cold and a CTA owns few of them), so the
+// kernels are organised around memory-level parallelism: (1) several CTAs per sample -- kCapSlices column /
+// unit slices for the caption attention, kVisSlices for the visual one, each recomputing the (cheap) scores;
+// (2) every thread requests a whole batch of independent 128-bit loads before it consumes the first one.
+constexpr int kRowBatch = 9;
+
+// scores s_j = w . act(att1_j + a2) + bias for the n rows of one sample, into sc[] (shared).  A warp takes up to 3
+// rows at a time and requests every piece of them before using any.
+template <bool kTanh>
+__device__ __forceinline__ void attn_scores(const float* __restrict__ att1, int n, int A, const float* a2, const float* wv,
+                                            float bias, float* sc) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int A4 = A >> 2;
+  const float4* a2v = reinterpret_cast<const float4*>(a2);
+  const float4* wvv = reinterpret_cast<const float4*>(wv);
+  for (int jb = wid; jb < n; jb += 3 * nw) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int xc = 0; xc < A4; xc += 128) {
+      float4 v[3][4];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int j = jb + r * nw;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x4 = xc + lane + 32 * k;
+          v[r][k] = (j < n && x4 < A4) ? __ldg(reinterpret_cast<const float4*>(att1 + (long)j * A) + x4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int x4 = xc + lane + 32 * k;
+          if (x4 >= A4) continue;
+          const float4 b = a2v[x4], ww = wvv[x4], y = v[r][k];
+          if (kTanh) {
+            acc[r] += ww.x * tanhf(y.x + b.x) + ww.y * tanhf(y.y + b.y) + ww.z * tanhf(y.z + b.z) + ww.w * tanhf(y.w + b.w);
+          } else {
+            acc[r] += ww.x * fmaxf(y.x + b.x, 0.f) + ww.y * fmaxf(y.y + b.y, 0.f) + ww.z * fmaxf(y.z + b.z, 0.f) +
+                      ww.w * fmaxf(y.w + b.w, 0.f);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int j = jb + r * nw;
+      if (j >= n) continue;          // warp-uniform
+      const float sv = warp_sum(acc[r]) + bias;
+      if (lane == 0) sc[j] = sv;
+    }
+  }
+}
+
+// out[c] = sum_{r < nrows} alpha[r] * rows[r][c] for the float4 columns [c0, c1).  Threads = (column, row group);
+// each thread batches kRowBatch row loads; the groups' partial sums meet in `part` (blockDim float4 of shared memory).
+__device__ __forceinline__ void attn_weighted_rows(const float* __restrict__ rows, long row_stride, int nrows, int c0, int c1,
+                                                   const float* alpha, float* __restrict__ out, float4* part) {
+  const int tid = threadIdx.x;
+  const int cw = min(c1 - c0, (int)blockDim.x);
+  if (cw <= 0) return;
+  const int G = blockDim.x / cw;
+  const int g = tid / cw, c = tid % cw;
+  for (int cb = c0; cb < c1; cb += cw) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = cb + c;
+    if (g < G && col < c1) {
+      for (int r0 = g; r0 < nrows; r0 += G * kRowBatch) {
+        float4 v[kRowBatch];
+#pragma unroll
+        for (int k = 0; k < kRowBatch; ++k) {
+          const int r = r0 + k * G;
+          v[k] = (r < nrows) ? __ldg(reinterpret_cast<const float4*>(rows + (long)r * row_stride) + col)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < kRowBatch; ++k) {
+          const int r = r0 + k * G;
+          const float al = (r < nrows) ? alpha[r] : 0.f;
+          acc.x += al * v[k].x; acc.y += al * v[k].y; acc.z += al * v[k].z; acc.w += al * v[k].w;
+        }
+      }
+    }
+    part[tid] = acc;
+    __syncthreads();
+    if (g == 0 && col < c1) {
+      for (int k = 1; k < G; ++k) {
+        const float4 v = part[k * cw + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(out)[col] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// grid (b, cap_slices + vis_slices).  y < cap_slices: caption attention (editnet.py:370-376) + select (:409-421) for
+// a column slice of D;  y >= cap_slices: visual attention (:442-446; adaptive :449-456) for a column slice of F.
+// dynamic smem: a2[A] | wv[A] | sc[max(P,R) padded] | part[4 * blockDim]
+__global__ void __launch_bounds__(kAttnThreads, 3) attention_fwd_kernel(const AttnFwdArgs a, int cap_slices) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
   const int A = a.A;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool cap = ((int)blockIdx.y < cap_slices);
+  const int n = cap ? a.P : a.R;
   float* a2 = sm;
   float* wv = sm + A;
   float* sc = sm + 2 * A;
-  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const bool cap = (blockIdx.y == 0);
-  if (cap && a.att1c == nullptr) return;
-  if (!cap && a.att1v == nullptr) return;
-  const int n = cap ? a.P : a.R;
+  float4* part = reinterpret_cast<float4*>(sm + 2 * A + ((max(a.P, a.R) + 3) & ~3));
   const float* att1 = cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A;
   const float* s2row = a.s2 + (long)i * a.ld_s2 + (cap ? 0 : A);
   const float* w = cap ? a.cap_w : a.vis_w;
@@ -340,26 +436,19 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnF
   for (int x = tid; x < A; x += blockDim.x) { a2[x] = s2row[x]; wv[x] = w[x]; }
   __syncthreads();
   const int nvalid = cap ? n : (a.nreg ? a.nreg[i] : n);
-  for (int j = wid; j < n; j += nw) {
-    float s = 0.f;
-    const float* row = att1 + (long)j * A;
-    if (cap) {
-#pragma unroll 4
-      for (int x = lane; x < A; x += 32) s += wv[x] * tanhf(row[x] + a2[x]);
-    } else {
-#pragma unroll 4
-      for (int x = lane; x < A; x += 32) s += wv[x] * fmaxf(row[x] + a2[x], 0.f);
-    }
-    s = warp_sum(s) + bias;
-    if (cap) { if (a.mask[(long)i * a.P + j] == 0.f) s = kNegFill; }
-    else if (j >= nvalid) s = kNegFill;
-    if (lane == 0) sc[j] = s;
-  }
+  if (cap) attn_scores<true>(att1, n, A, a2, wv, bias, sc);
+  else attn_scores<false>(att1, n, A, a2, wv, bias, sc);
   __syncthreads();
-  // softmax (+ argmax) by warp 0
+  // mask, softmax by warp 0
   if (wid == 0) {
     float m = -INFINITY;
-    for (int j = lane; j < n; j += 32) m = fmaxf(m, sc[j]);
+    for (int j = lane; j < n; j += 32) {
+      float v = sc[j];
+      if (cap) { if (a.mask[(long)i * a.P + j] == 0.f) v = kNegFill; }
+      else if (j >= nvalid) v = kNegFill;
+      sc[j] = v;
+      m = fmaxf(m, v);
+    }
     m = warp_max(m);
     float sum = 0.f;
     for (int j = lane; j < n; j += 32) { const float e = expf(sc[j] - m); sc[j] = e; sum += e; }
@@ -367,139 +456,105 @@ __global__ void __launch_bounds__(kAttnThreads) attention_fwd_kernel(const AttnF
     for (int j = lane; j < n; j += 32) sc[j] = sc[j] / sum;
   }
   __syncthreads();
-  float* alpha_out = cap ? a.alpha_c + (long)i * a.P : a.alpha_v + (long)i * a.R;
-  if (blockIdx.y <= 1)
-    for (int j = tid; j < n; j += blockDim.x) alpha_out[j] = sc[j];
   if (cap) {
-    const float* ph = a.prev_h + (long)i * a.P * a.D;
-    for (int d = tid; d < a.D; d += blockDim.x) {
-      float c = 0.f;
-#pragma unroll 6
-      for (int j = 0; j < n; ++j) c += sc[j] * ph[(long)j * a.D + d];
-      a.ctx[(long)i * (a.ld_ctx ? a.ld_ctx : a.D) + d] = c;
-    }
+    const int sl = blockIdx.y;
+    if (sl == 0)
+      for (int j = tid; j < n; j += blockDim.x) a.alpha_c[(long)i * a.P + j] = sc[j];
+    const int D4 = a.D >> 2;
+    const int per = (D4 + cap_slices - 1) / cap_slices;
+    const int c0 = sl * per, c1 = min(D4, c0 + per);
+    attn_weighted_rows(a.prev_h + (long)i * a.P * a.D, a.D, n, c0, c1, sc, a.ctx + (long)i * (a.ld_ctx ? a.ld_ctx : a.D), part);
     if (a.prev_m) {
       int js = 0; float best = sc[0];
       for (int j = 1; j < n; ++j) if (sc[j] > best) { best = sc[j]; js = j; }
       const float wsel = best + (1.f - best);
-      const float* pm = a.prev_m + ((long)i * a.P + js) * a.D;
-      for (int d = tid; d < a.D; d += blockDim.x) a.sel[(long)i * a.D + d] = wsel * pm[d];
-      if (tid == 0) a.sel_idx[i] = js;
+      const float4* pm = reinterpret_cast<const float4*>(a.prev_m + ((long)i * a.P + js) * a.D);
+      float4* so = reinterpret_cast<float4*>(a.sel + (long)i * a.D);
+      for (int c = c0 + tid; c < c1; c += blockDim.x) {
+        const float4 v = __ldg(pm + c);
+        so[c] = make_float4(wsel * v.x, wsel * v.y, wsel * v.z, wsel * v.w);
+      }
+      if (sl == 0 && tid == 0) a.sel_idx[i] = js;
     }
   } else {
-    const float* ft = a.feats + (long)i * a.R * a.F;
-    float* out = a.att_img + (long)i * a.ld_img;
+    const int slices = gridDim.y - cap_slices, sl = blockIdx.y - cap_slices;
+    if (sl == 0)
+      for (int j = tid; j < n; j += blockDim.x) a.alpha_v[(long)i * a.R + j] = sc[j];
     const int F4 = a.F >> 2;
-    const int slices = gridDim.y - 1, vs = blockIdx.y - 1;
     const int per = (F4 + slices - 1) / slices;
-    const int c0 = vs * per, c1 = min(F4, c0 + per);
-    // threads = (column, row group): the regions of a column are split over G groups whose partial sums meet
-    // in shared memory, so every thread keeps ~R/G independent 128-bit loads in flight
-    float4* part = reinterpret_cast<float4*>(sm + 2 * A + ((n + 3) & ~3) + 40);
-    const int cw = min(per, (int)blockDim.x);
-    const int G = blockDim.x / cw;
-    const int g = tid / cw, c = tid % cw;
-    for (int cb = c0; cb < c1; cb += cw) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int col = cb + c;
-      if (g < G && col < c1) {
-#pragma unroll 9
-        for (int r = g; r < nvalid; r += G) {
-          const float al = sc[r];
-          const float4 v = __ldg(reinterpret_cast<const float4*>(ft + (long)r * a.F) + col);
-          acc.x += al * v.x; acc.y += al * v.y; acc.z += al * v.z; acc.w += al * v.w;
-        }
-      }
-      part[tid] = acc;
-      __syncthreads();
-      if (g == 0 && col < c1) {
-        for (int k = 1; k < G; ++k) {
-          const float4 v = part[k * cw + c];
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        reinterpret_cast<float4*>(out)[col] = acc;
-      }
-      __syncthreads();
-    }
+    const int c0 = sl * per, c1 = min(F4, c0 + per);
+    attn_weighted_rows(a.feats + (long)i * a.R * a.F, a.F, nvalid, c0, c1, sc, a.att_img + (long)i * a.ld_img, part);
   }
 }
 
 // Attention backward runs as two chained kernels so that no CTA has to pull a whole sample through one SM:
-//   (1) attention_bwd_dal_kernel: d alpha_j = <d context, value_j> (+ select term); grid (b, 1 + slices), the
-//       visual rows are dealt round-robin to `slices` CTAs; results go to a small global scratch;
-//   (2) attention_bwd_main_kernel: softmax backward (recomputed by every CTA of the sample: n <= 100 values),
-//       then y == 0: value gradients of the caption attention (d prev_h, d prev_m);
-//            y in [1, 1+cs): unit slices of the caption score MLP;  y >= 1+cs: unit slices of the visual score MLP.
-__global__ void __launch_bounds__(kAttnThreads) attention_bwd_dal_kernel(const AttnBwdArgs a, float* __restrict__ dal_out) {
+//   (1) attention_bwd_dal_kernel: d alpha_j = <d context, value_j> (+ select term); the rows of a sample are dealt
+//       round-robin to the sample's CTAs; results go to a small global scratch;
+//   (2) attention_bwd_main_kernel: softmax backward (recomputed by every CTA of the sample: n <= 100 values), then a
+//       unit slice of the score MLP; the caption CTAs also share the value gradients (d prev_h, d prev_m).
+__global__ void __launch_bounds__(kAttnThreads, 3) attention_bwd_dal_kernel(const AttnBwdArgs a, float* __restrict__ dal_out,
+                                                                            int cap_slices) {
   pdl_trigger();
   pdl_wait();
-  const bool cap = (blockIdx.y == 0);
-  if (cap && a.att1c == nullptr) return;
-  if (!cap && a.att1v == nullptr) return;
+  const bool cap = ((int)blockIdx.y < cap_slices);
   const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   float* dal = dal_out + (long)i * (a.P + a.R);
-  if (cap) {
-    const int js = a.dsel ? a.sel_idx[i] : -1;
-    const float* ph = a.prev_h + (long)i * a.P * a.D;
-    const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
-    for (int j = wid; j < a.P; j += nw) {
-      float s = 0.f;
-      {
-        const float4* x4 = reinterpret_cast<const float4*>(dc);
-        const float4* y4 = reinterpret_cast<const float4*>(ph + (long)j * a.D);
-#pragma unroll 8
-        for (int d = lane; d < a.D / 4; d += 32) {
-          const float4 x = x4[d], y = __ldg(y4 + d);
-          s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-        }
-      }
-      if (j == js) {
-        const float4* y4 = reinterpret_cast<const float4*>(a.prev_m + ((long)i * a.P + j) * a.D);
-        const float4* x4 = reinterpret_cast<const float4*>(a.dsel + (long)i * a.D);
-#pragma unroll 8
-        for (int d = lane; d < a.D / 4; d += 32) {
-          const float4 x = x4[d], y = __ldg(y4 + d);
-          s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-        }
-      }
-      s = warp_sum(s);
-      if (lane == 0) dal[j] = s;
-    }
-  } else {
-    const int slices = gridDim.y - 1, vs = blockIdx.y - 1;
-    const int nvalid = a.nreg ? a.nreg[i] : a.R;
-    const float* ft = a.feats + (long)i * a.R * a.F;
-    const float* di = a.datt_img + (long)i * a.ld_dimg;
-    for (int r = vs + slices * wid; r < a.R; r += slices * nw) {
+  // <x, y_r> for this CTA's rows: a warp per row, 8 x 128-bit loads per lane in flight
+  auto dots = [&](const float* __restrict__ x, const float* __restrict__ ybase, long ystride, int len4, int r_first, int r_step,
+                  int nrows, int nvalid, float* out, int js, const float* __restrict__ xs, const float* __restrict__ ys) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int r = r_first + r_step * wid; r < nrows; r += r_step * nw) {
       float s = 0.f;
       if (r < nvalid) {
-        const float4* x4 = reinterpret_cast<const float4*>(di);
-        const float4* y4 = reinterpret_cast<const float4*>(ft + (long)r * a.F);
-#pragma unroll 8
-        for (int f = lane; f < a.F / 4; f += 32) {
-          const float4 x = x4[f], y = __ldg(y4 + f);
-          s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        const float4* y4 = reinterpret_cast<const float4*>(ybase + (long)r * ystride);
+        for (int d0 = lane; d0 < len4; d0 += 32 * 8) {
+          float4 yv[8], xv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int d = d0 + 32 * k;
+            yv[k] = d < len4 ? __ldg(y4 + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[k] = d < len4 ? x4[d] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s += xv[k].x * yv[k].x + xv[k].y * yv[k].y + xv[k].z * yv[k].z + xv[k].w * yv[k].w;
+        }
+        if (r == js) {   // straight-through select term: <d sel, prev_m[js]>
+          const float4* y4s = reinterpret_cast<const float4*>(ys);
+          const float4* x4s = reinterpret_cast<const float4*>(xs);
+          for (int d = lane; d < len4; d += 32) {
+            const float4 xx = x4s[d], yy = __ldg(y4s + d);
+            s += xx.x * yy.x + xx.y * yy.y + xx.z * yy.z + xx.w * yy.w;
+          }
         }
       }
       s = warp_sum(s);
-      if (lane == 0) dal[a.P + r] = s;
+      if (lane == 0) out[r] = s;
     }
+  };
+  if (cap) {
+    const int js = a.dsel ? a.sel_idx[i] : -1;
+    dots(a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D), a.prev_h + (long)i * a.P * a.D, a.D, a.D >> 2, blockIdx.y, cap_slices,
+         a.P, a.P, dal, js, a.dsel ? a.dsel + (long)i * a.D : nullptr,
+         (a.dsel && js >= 0) ? a.prev_m + ((long)i * a.P + js) * a.D : nullptr);
+  } else {
+    const int slices = gridDim.y - cap_slices, sl = blockIdx.y - cap_slices;
+    const int nvalid = a.nreg ? a.nreg[i] : a.R;
+    dots(a.datt_img + (long)i * a.ld_dimg, a.feats + (long)i * a.R * a.F, a.F, a.F >> 2, sl, slices, a.R, nvalid, dal + a.P, -1,
+         nullptr, nullptr);
   }
 }
 
 // dynamic smem: a2[A] | wv[A] | al[n] | ds[n] | red[40] | part[2 * blockDim]
-__global__ void __launch_bounds__(kAttnThreads) attention_bwd_main_kernel(const AttnBwdArgs a, const float* __restrict__ dal_in,
-                                                                          int cap_slices) {
+__global__ void __launch_bounds__(kAttnThreads, 3) attention_bwd_main_kernel(const AttnBwdArgs a, const float* __restrict__ dal_in,
+                                                                             int cap_slices) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
   const int A = a.A;
   const int y = blockIdx.y;
-  const bool cap = (y < 1 + cap_slices);
-  if (cap && a.att1c == nullptr) return;
-  if (!cap && a.att1v == nullptr) return;
+  const bool cap = (y < cap_slices);
   const int n = cap ? a.P : a.R;
-  const int npad = (n + 3) & ~3;
+  const int npad = (max(a.P, a.R) + 3) & ~3;
   float* a2 = sm;
   float* wv = sm + A;
   float* al = sm + 2 * A;
@@ -528,39 +583,53 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_main_kernel(const 
     dsum += v;
   }
   const float dbias = block_sum(dsum, red);  // also orders ds[] writes before the reads below
-  if (y == 0) {
-    // value gradients of the caption attention (+ the bias gradient, once per sample)
-    if (tid == 0) atomicAdd(a.dcap_b, dbias);
-    const int js = a.dsel ? a.sel_idx[i] : -1;
-    const float* dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
-    float* dph = a.dprev_h + (long)i * a.P * a.D;
+  const int slices = cap ? cap_slices : (int)gridDim.y - cap_slices;
+  const int sl = cap ? y : y - cap_slices;
+  if (sl == 0 && tid == 0) atomicAdd(cap ? a.dcap_b : a.dvis_b, dbias);
+  if (cap) {
+    // value gradients, rows dealt round-robin to the caption CTAs: d prev_h[j] += alpha_j * d ctx
+    const float* __restrict__ dc = a.dctx + (long)i * (a.ld_dctx ? a.ld_dctx : a.D);
+    float* __restrict__ dph = a.dprev_h + (long)i * a.P * a.D;
     const int D4 = a.D >> 2;
-    for (int e = tid; e < n * D4; e += blockDim.x) {
-      const int j = e / D4, d4 = e % D4;
-      const float4 g = reinterpret_cast<const float4*>(dc)[d4];
-      float4* dst = reinterpret_cast<float4*>(dph + (long)j * a.D) + d4;
-      float4 v = *dst;
-      const float aj = al[j];
-      v.x += aj * g.x; v.y += aj * g.y; v.z += aj * g.z; v.w += aj * g.w;
-      *dst = v;
+    const int nrow = (n - sl + slices - 1) / slices;          // rows sl, sl + slices, ...
+    const int items = nrow * D4;
+    for (int e0 = tid; e0 < items; e0 += blockDim.x * kRowBatch) {
+      float4 old[kRowBatch], g[kRowBatch];
+#pragma unroll
+      for (int k = 0; k < kRowBatch; ++k) {
+        const int e = e0 + k * blockDim.x;
+        if (e < items) {
+          const int j = sl + slices * (e / D4), d4 = e % D4;
+          old[k] = *(reinterpret_cast<const float4*>(dph + (long)j * a.D) + d4);
+          g[k] = reinterpret_cast<const float4*>(dc)[d4];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kRowBatch; ++k) {
+        const int e = e0 + k * blockDim.x;
+        if (e < items) {
+          const int j = sl + slices * (e / D4), d4 = e % D4;
+          const float aj = al[j];
+          float4 v = old[k];
+          v.x += aj * g[k].x; v.y += aj * g[k].y; v.z += aj * g[k].z; v.w += aj * g[k].w;
+          *(reinterpret_cast<float4*>(dph + (long)j * a.D) + d4) = v;
+        }
+      }
     }
-    if (js >= 0) {
+    const int js = a.dsel ? a.sel_idx[i] : -1;
+    if (js >= 0 && sl == 0) {
       const float best = al[js];
       const float wsel = best + (1.f - best);
       float* dpm = a.dprev_m + ((long)i * a.P + js) * a.D;
       const float* dsl = a.dsel + (long)i * a.D;
       for (int d = tid; d < a.D; d += blockDim.x) dpm[d] += wsel * dsl[d];
     }
-    return;
   }
-  // score-MLP backward for a slice of the attention units: threads = (unit, row group)
-  const int slices = cap ? cap_slices : (int)gridDim.y - 1 - cap_slices;
-  const int sl = cap ? y - 1 : y - 1 - cap_slices;
-  if (!cap && sl == 0 && tid == 0) atomicAdd(a.dvis_b, dbias);
+  // score-MLP backward for a slice of the attention units: threads = (unit, row group), rows in batches
   const int per = (A + slices - 1) / slices;
   const int x0 = sl * per, x1 = min(A, x0 + per);
-  const float* att1 = cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A;
-  float* datt1 = cap ? a.datt1c + (long)i * a.P * A : a.datt1v + (long)i * a.R * A;
+  const float* __restrict__ att1 = cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A;
+  float* __restrict__ datt1 = cap ? a.datt1c + (long)i * a.P * A : a.datt1v + (long)i * a.R * A;
   const bool accum = cap ? true : (a.datt1v_accum != 0);
   float* ds2row = a.ds2 + (long)i * a.ld_ds2 + (cap ? 0 : A);
   float* dwv = cap ? a.dcap_w : a.dvis_w;
@@ -572,15 +641,26 @@ __global__ void __launch_bounds__(kAttnThreads) attention_bwd_main_kernel(const 
     float d2 = 0.f, dw = 0.f;
     if (g < G && x < x1) {
       const float av = a2[x], wx = wv[x];
-#pragma unroll 4
-      for (int j = g; j < n; j += G) {
-        const float pre = att1[(long)j * A + x] + av;
-        float yv, dpre;
-        if (cap) { yv = tanhf(pre); dpre = ds[j] * wx * (1.f - yv * yv); }
-        else { yv = fmaxf(pre, 0.f); dpre = (pre > 0.f) ? ds[j] * wx : 0.f; }
-        dw += ds[j] * yv;
-        d2 += dpre;
-        if (accum) datt1[(long)j * A + x] += dpre; else datt1[(long)j * A + x] = dpre;
+      for (int j0 = g; j0 < n; j0 += G * kRowBatch) {
+        float pre[kRowBatch], old[kRowBatch];
+#pragma unroll
+        for (int k = 0; k < kRowBatch; ++k) {
+          const int j = j0 + k * G;
+          pre[k] = (j < n) ? att1[(long)j * A + x] : 0.f;
+          old[k] = (accum && j < n) ? datt1[(long)j * A + x] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kRowBatch; ++k) {
+          const int j = j0 + k * G;
+          if (j >= n) continue;
+          const float pv = pre[k] + av;
+          float yv, dpre;
+          if (cap) { yv = tanhf(pv); dpre = ds[j] * wx * (1.f - yv * yv); }
+          else { yv = fmaxf(pv, 0.f); dpre = (pv > 0.f) ? ds[j] * wx : 0.f; }
+          dw += ds[j] * yv;
+          d2 += dpre;
+          datt1[(long)j * A + x] = old[k] + dpre;
+        }
       }
     }
     part[2 * tid] = d2; part[2 * tid + 1] = dw;
@@ -872,11 +952,13 @@ int enc_mask(const float* prev_m, float* mask, int B, int P, int D, cudaStream_t
 }
 int attention_fwd(const AttnFwdArgs& a, cudaStream_t s) {
   if (a.b <= 0) return SET_OK;
-  SET_REQUIRE(a.F % 4 == 0, "F % 4");
+  SET_REQUIRE(a.F % 4 == 0 && a.D % 4 == 0 && a.A % 4 == 0, "D, A, F % 4");
   const int n = a.P > a.R ? a.P : a.R;
-  const size_t smem = sizeof(float) * (2 * a.A + ((n + 3) & ~3) + 40 + 4 * kAttnThreads);
+  const size_t smem = sizeof(float) * (2 * a.A + ((n + 3) & ~3) + 4 * kAttnThreads);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  SET_CHECK_CUDA(launch_chain(attention_fwd_kernel, dim3(a.b, 1 + (a.att1v ? kVisSlices : 0)), dim3(kAttnThreads), smem, s, a));
+  const int cs = a.att1c ? kCapSlices : 0, vs = a.att1v ? kVisSlices : 0;
+  if (cs + vs == 0) return SET_OK;
+  SET_CHECK_CUDA(launch_chain(attention_fwd_kernel, dim3(a.b, cs + vs), dim3(kAttnThreads), smem, s, a, cs));
   LAUNCH_OK();
 }
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
@@ -893,11 +975,11 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
     dal_cap = need < 65536 ? 65536 : 2 * need;
     SET_CHECK_CUDA(cudaMalloc(&dal, sizeof(float) * dal_cap));
   }
-  const int vis = a.att1v ? kVisSlices : 0;
-  const int cs = 2;   // unit slices of the caption score MLP
-  SET_CHECK_CUDA(launch_chain(attention_bwd_dal_kernel, dim3(a.b, 1 + vis), dim3(kAttnThreads), 0, s, a, dal));
+  const int cs = a.att1c ? kCapSlices : 0, vs = a.att1v ? kVisSlices : 0;
+  if (cs + vs == 0) return SET_OK;
+  SET_CHECK_CUDA(launch_chain(attention_bwd_dal_kernel, dim3(a.b, cs + vs), dim3(kAttnThreads), 0, s, a, dal, cs));
   set_count_launch(1);
-  SET_CHECK_CUDA(launch_chain(attention_bwd_main_kernel, dim3(a.b, 1 + cs + vis), dim3(kAttnThreads), smem, s, a,
+  SET_CHECK_CUDA(launch_chain(attention_bwd_main_kernel, dim3(a.b, cs + vs), dim3(kAttnThreads), smem, s, a,
                               (const float*)dal, cs));
   LAUNCH_OK();
 }
