@@ -173,7 +173,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int QN>
+// TWIN = 1: a shallower pipeline sized so that TWO CTAs share an SM (half the shared memory, 256 tensor-memory
+// columns each).  Used for the big time-batched GEMMs (many tiles per SM): one CTA's prologue / epilogue / MMA
+// drain overlaps the other's main loop, and twice as many converter warps feed the tensor core.
+template <int QN, int TWIN = 0>
 struct TcCfg {
   // Two rings.  P: raw fp32 tiles of the 128-row operand; a K-block of P is converted straight into tensor
   // memory, so the ring only has to cover the HBM latency -- it is the deep one (Little: 148 SMs x kNP x 16 KB
@@ -183,13 +186,17 @@ struct TcCfg {
 #define SET_TC_NQ64 6
 #define SET_TC_NP64 6
 #endif
-  static constexpr int kNQ = (QN <= 64) ? SET_TC_NQ64 : 3;
-  static constexpr int kNP = (QN <= 64) ? SET_TC_NP64 : 6;
+  static constexpr int kNQ = TWIN ? 2 : ((QN <= 64) ? SET_TC_NQ64 : 3);
+  static constexpr int kNP = TWIN ? 3 : ((QN <= 64) ? SET_TC_NP64 : 6);
+  static constexpr uint32_t kTmemCols = TWIN ? 256u : 512u;
+  static_assert(!TWIN || QN == 128, "the twin configuration is built for 128-wide Q tiles");
   static constexpr int kPBytes = kTileP * 128;
   static constexpr int kQBytes = QN * 128;
   static constexpr int kQSlot = 2 * kQBytes;
   static constexpr int kRingBytes = kNP * kPBytes + kNQ * kQSlot;
-  static constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // (the twin configuration has no room for alignment slack: the kernel keeps no static shared memory, so the
+  // dynamic window starts 1024-aligned; the kernel traps if that ever stops being true)
+  static constexpr int kSmemBytes = kRingBytes + (TWIN ? 0 : 1024) /*align*/ + 256 /*barriers*/;
 };
 
 template <int G>
@@ -199,9 +206,9 @@ struct TcGroup {
   TcParams p[G];
 };
 
-template <int QN, int G>
-__global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_constant__ TcGroup<G> grp) {
-  using Cfg = TcCfg<QN>;
+template <int QN, int G, int TWIN = 0>
+__global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const __grid_constant__ TcGroup<G> grp) {
+  using Cfg = TcCfg<QN, TWIN>;
   int pi = 0;
   while (pi + 1 < grp.n && (int)blockIdx.x >= grp.cta_start[pi + 1]) ++pi;
   const TcParams& prm = grp.p[pi];
@@ -217,6 +224,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   const uint32_t accum_bar = bar_base + 8u * (NP + 3 * NQ);
   const uint32_t tmem_slot = bar_base + 8u * (NP + 3 * NQ + 1);
   uint8_t* gen_base = smem_dyn + (base - smem_u32(smem_dyn));
+  if (TWIN && base != smem_u32(smem_dyn)) __trap();
+  volatile int* s_last_p = reinterpret_cast<volatile int*>(gen_base + (bar_base - base) + 8 * (NP + 3 * NQ + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 64) TC_STAMP(0);
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(Cfg::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -447,7 +456,6 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
       // its partners and finishes 1/split of the tile's items; otherwise the last CTA to arrive finishes all.
       // An item gathers every partial + bias/add/C operand it needs with independent 128-bit loads issued
       // together (one L2 round trip), applies the cell, and stores.  Summation order is fixed (split 0, 1, ..).
-      __shared__ int s_last;
       constexpr int kSlab = QN * kTileP;
       const int rows = prm.Qr < QN ? prm.Qr : QN;
       const int split = prm.split_k;
@@ -471,15 +479,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
               __nanosleep(40);
               asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
             }
-            s_last = 1;
+            *s_last_p = 1;
           } else {
             const int last = (old == split - 1) ? 1 : 0;
             if (last) *cnt = 0;   // every partner has arrived; the next launch finds the counter at zero
-            s_last = last;
+            *s_last_p = last;
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");
-        finisher = (s_last != 0);
+        finisher = (*s_last_p != 0);
         if (prm.coop) { nfin = split; fin = ks; }
         if (ct == 0) TC_STAMP(10);
         __threadfence();
@@ -686,7 +694,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gemm_tc_kernel(const __grid_con
   if (threadIdx.x == 64) TC_STAMP(8);
   if (prm.trace && threadIdx.x == 0 && blockIdx.x < 1000) prm.trace[17 + 2 * blockIdx.x] = gtimer();   // per-CTA end
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -721,6 +729,8 @@ void tc_init() {
   set_attr(gemm_tc_kernel<64, 2>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 2>, TcCfg<128>::kSmemBytes);
   set_attr(gemm_tc_kernel<64, 5>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 5>, TcCfg<128>::kSmemBytes);
   set_attr(gemm_tc_kernel<64, 8>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8>, TcCfg<128>::kSmemBytes);
+  set_attr(gemm_tc_kernel<128, 1, 1>, TcCfg<128, 1>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 2, 1>, TcCfg<128, 1>::kSmemBytes);
+  set_attr(gemm_tc_kernel<128, 5, 1>, TcCfg<128, 1>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8, 1>, TcCfg<128, 1>::kSmemBytes);
   ok = ok && cudaMalloc(&g_tc_scratch, sizeof(float) * (size_t)kScratchSlots * kTileP * 128) == cudaSuccess;
   // (+ 16 bytes of zeros behind the counters: TcParams::zero16)
   ok = ok && cudaMalloc(&g_tc_counters, sizeof(int) * (2 * kScratchSlots + 4)) == cudaSuccess;
@@ -920,6 +930,12 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     memcpy(small.cta_start, grp.cta_start, sizeof(small.cta_start));
     memcpy(small.p, grp.p, sizeof(TcParams) * grp.n);
     if (QN == 64) return launch_chain(gemm_tc_kernel<64, G>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, small);
+    // many tiles per SM and no fused epilogue in play: two CTAs per SM (see TcCfg)
+    static const int twin_on = getenv("SET_TC_TWIN") ? atoi(getenv("SET_TC_TWIN")) : 1;
+    bool any_fused = false;
+    for (int k = 0; k < grp.n; ++k) any_fused = any_fused || grp.p[k].fused;
+    if (twin_on && !any_fused && cta > g_sm_count)
+      return launch_chain(gemm_tc_kernel<128, G, 1>, dim3(cta), dim3(kThreadsTc), TcCfg<128, 1>::kSmemBytes, stream, small);
     return launch_chain(gemm_tc_kernel<128, G>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, small);
   };
   cudaError_t lerr;
