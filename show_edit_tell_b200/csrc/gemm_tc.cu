@@ -39,6 +39,12 @@ namespace {
 
 constexpr int kBlockK = 32;        // fp32 per smem row: 128 B = one swizzle span
 constexpr int kTileP = 128;        // UMMA M
+// 1: the "hi" operand is the raw fp32 word -- kind::tf32 reads only sign, exponent and the top 10 mantissa bits
+// of each 32-bit container, so masking the low 13 bits first changes nothing and the write-back of Q_hi is saved.
+// (Verified on B200 by the parity tests: a rounding datapath would show as ~1e-3 errors.)
+#ifndef SET_TC_RAW_HI
+#define SET_TC_RAW_HI 1
+#endif
 #ifndef SET_TC_CONV_WARPS
 #define SET_TC_CONV_WARPS 8
 #endif
@@ -372,7 +378,9 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
         const float4 v = q_hi[gt + kGT * j];
         float4 h, l;
         split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
+#if !SET_TC_RAW_HI
         q_hi[gt + kGT * j] = h;
+#endif
         q_lo[gt + kGT * j] = l;
       }
       // P (the 128-row operand) goes to tensor memory: this thread owns tile row `prow` = its TMEM lane, reads
@@ -393,10 +401,10 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
           const int cch = half * 4 + cc;
           const float4 v = p_raw[prow * 8 + (cch ^ (prow & 7))];
           float h, l;
-          split(v.x, h, l); hi[cc * 4 + 0] = __float_as_uint(h); lo[cc * 4 + 0] = __float_as_uint(l);
-          split(v.y, h, l); hi[cc * 4 + 1] = __float_as_uint(h); lo[cc * 4 + 1] = __float_as_uint(l);
-          split(v.z, h, l); hi[cc * 4 + 2] = __float_as_uint(h); lo[cc * 4 + 2] = __float_as_uint(l);
-          split(v.w, h, l); hi[cc * 4 + 3] = __float_as_uint(h); lo[cc * 4 + 3] = __float_as_uint(l);
+          split(v.x, h, l); hi[cc * 4 + 0] = __float_as_uint(SET_TC_RAW_HI ? v.x : h); lo[cc * 4 + 0] = __float_as_uint(l);
+          split(v.y, h, l); hi[cc * 4 + 1] = __float_as_uint(SET_TC_RAW_HI ? v.y : h); lo[cc * 4 + 1] = __float_as_uint(l);
+          split(v.z, h, l); hi[cc * 4 + 2] = __float_as_uint(SET_TC_RAW_HI ? v.z : h); lo[cc * 4 + 2] = __float_as_uint(l);
+          split(v.w, h, l); hi[cc * 4 + 3] = __float_as_uint(SET_TC_RAW_HI ? v.w : h); lo[cc * 4 + 3] = __float_as_uint(l);
         }
         tmem_st16(ta + (uint32_t)half * 16u, hi);
         tmem_st16(ta + 32u + (uint32_t)half * 16u, lo);
