@@ -815,6 +815,55 @@ __global__ void transpose_kernel(const float* __restrict__ in, long ld_in, float
     if (c < cols && r < rows) out[(long)c * ld_out + r] = tile[threadIdx.x][j];
   }
 }
+// up to kTrMaxJobs transposes in one grid: 64x64 tiles through shared memory, 128-bit accesses on both sides
+__global__ void __launch_bounds__(256) transpose_batch_kernel(const __grid_constant__ TrBatch b) {
+  __shared__ float tile[64][65];
+  int ji = 0;
+  while (ji + 1 < b.n && (int)blockIdx.x >= b.j[ji + 1].tile0) ++ji;
+  const TrJob& J = b.j[ji];
+  const int t = blockIdx.x - J.tile0;
+  const int r0 = (t / J.tiles_c) * 64, c0 = (t % J.tiles_c) * 64;
+  const int tid = threadIdx.x, q = tid >> 4, l4 = (tid & 15) * 4;
+  const bool vin = (J.ld_in % 4 == 0) && ((reinterpret_cast<uintptr_t>(J.in) & 15) == 0);
+  const bool vout = (J.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(J.out) & 15) == 0);
+  float4 v[4];
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int r = r0 + ps * 16 + q, c = c0 + l4;
+    v[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < J.rows) {
+      const float* src = J.in + (long)r * J.ld_in + c;
+      if (vin && c + 3 < J.cols) v[ps] = __ldg(reinterpret_cast<const float4*>(src));
+      else {
+        if (c < J.cols) v[ps].x = src[0];
+        if (c + 1 < J.cols) v[ps].y = src[1];
+        if (c + 2 < J.cols) v[ps].z = src[2];
+        if (c + 3 < J.cols) v[ps].w = src[3];
+      }
+    }
+  }
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    float* trow = tile[ps * 16 + q];
+    trow[l4] = v[ps].x; trow[l4 + 1] = v[ps].y; trow[l4 + 2] = v[ps].z; trow[l4 + 3] = v[ps].w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int c = c0 + ps * 16 + q, r = r0 + l4;
+    if (c >= J.cols) continue;
+    const int cc = ps * 16 + q;
+    const float4 o = make_float4(tile[l4][cc], tile[l4 + 1][cc], tile[l4 + 2][cc], tile[l4 + 3][cc]);
+    float* dst = J.out + (long)c * J.ld_out + r;
+    if (vout && r + 3 < J.rows) *reinterpret_cast<float4*>(dst) = o;
+    else {
+      if (r < J.rows) dst[0] = o.x;
+      if (r + 1 < J.rows) dst[1] = o.y;
+      if (r + 2 < J.rows) dst[2] = o.z;
+      if (r + 3 < J.rows) dst[3] = o.w;
+    }
+  }
+}
 __global__ void sum_time_kernel(const float* __restrict__ x, float* __restrict__ out, int T, long n) {
   for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < n; y += (long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -1037,6 +1086,27 @@ int transpose_ld(const float* in, long ld_in, float* out, long ld_out, int rows,
   if (rows <= 0 || cols <= 0) return SET_OK;
   transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, s>>>(in, ld_in, out, ld_out, rows, cols);
   LAUNCH_OK();
+}
+int transpose_batch(const TrJob* jobs, int n, cudaStream_t s) {
+  int i = 0;
+  while (i < n) {
+    TrBatch b;
+    b.n = 0;
+    int tiles = 0;
+    for (; i < n && b.n < kTrMaxJobs; ++i) {
+      if (jobs[i].rows <= 0 || jobs[i].cols <= 0) continue;
+      TrJob j = jobs[i];
+      j.tiles_c = (j.cols + 63) / 64;
+      j.tile0 = tiles;
+      tiles += j.tiles_c * ((j.rows + 63) / 64);
+      b.j[b.n++] = j;
+    }
+    if (b.n == 0) break;
+    transpose_batch_kernel<<<tiles, 256, 0, s>>>(b);
+    SET_CHECK_CUDA(cudaGetLastError());
+    set_count_launch(1);
+  }
+  return SET_OK;
 }
 int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s) {
   sum_time_kernel<<<blocks_for(BN, kThreads), kThreads, 0, s>>>(x, out, T, BN);

@@ -142,6 +142,11 @@ int dropout_fwd(const float* x, float* out, int rows, int D, int train, uint64_t
 int transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);
 // strided form: out[c*ld_out + r] = in[r*ld_in + c]
 int transpose_ld(const float* in, long ld_in, float* out, long ld_out, int rows, int cols, cudaStream_t s);
+// several transposes in one launch: out[c * ld_out + r] = in[r * ld_in + c]
+constexpr int kTrMaxJobs = 24;
+struct TrJob { const float* in; long ld_in; float* out; long ld_out; int rows, cols; int tile0, tiles_c; };
+struct TrBatch { int n; TrJob j[kTrMaxJobs]; };
+int transpose_batch(const TrJob* jobs, int n, cudaStream_t s);
 // sum over time of a [T][B][N] buffer -> [B][N]
 int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s);
 // materialise keep bits as floats (tests): out[i] = keep(seed, site, base+i)

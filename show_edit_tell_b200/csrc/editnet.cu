@@ -453,7 +453,10 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
         {w.al_whh, s.t_al_whh, 4 * D, D}, {w.al_wih, s.t_al_wih, 4 * D, 3 * D + F}, {w.cl_h2h_w, s.t_cl_h2h, 4 * D, D},
         {w.ca_feat_w, s.t_ca_feat, A, D}, {w.va_feat_w, s.t_va_feat, A, D}, {w.enc_aff_w, s.t_enc_aff, D, D},
         {w.enc_h2h_w, s.t_enc_h2h, 4 * D, D}, {w.enc_x2h_w, s.t_enc_x2h, 4 * D, D}};
-    for (auto& e : tr) SET_PROPAGATE(transpose(e.w, e.t, e.O, e.I, st));
+    TrJob jobs[17];
+    int nj = 0;
+    for (auto& e : tr) jobs[nj++] = TrJob{e.w, (long)e.I, e.t, (long)e.O, e.O, e.I, 0, 0};
+    SET_PROPAGATE(transpose_batch(jobs, nj, st));
   }
   // one dX term: out[m][j] += sum_o dY[m][o] * W[o][c0 + j]   (W is [O][I])
   auto dx = [&](GemmProblem& p, const float* dY, long ldy, const float* W, const float* WTp, int O, int I, int c0) {
@@ -565,6 +568,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   // transposed once per backward call into `tscratch`.
   struct TrEntry { const float* src; long ld; int rows, cols; const float* dst; };
   std::vector<TrEntry> tr_cache;
+  std::vector<TrJob> tr_pending;
   size_t tr_used = 0;
   int tr_err = SET_OK;
   auto TR = [&](const float* X, long ld, int rows, int cols) -> const float* {
@@ -574,10 +578,15 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     if (tr_used + rp * cols > s.tscratch_floats) { tr_err = SET_ERR_WORKSPACE; return nullptr; }
     float* dst = s.tscratch + tr_used;
     tr_used += rp * cols;
-    const int r = transpose_ld(X, ld, dst, (long)rp, rows, cols, st);
-    if (r != SET_OK) tr_err = r;
+    tr_pending.push_back(TrJob{X, ld, dst, (long)rp, rows, cols, 0, 0});   // launched by flush_tr(), batched
     tr_cache.push_back({X, ld, rows, cols, dst});
     return dst;
+  };
+  auto flush_tr = [&]() -> int {
+    if (tr_pending.empty()) return SET_OK;
+    const int r = transpose_batch(tr_pending.data(), (int)tr_pending.size(), st);
+    tr_pending.clear();
+    return r;
   };
   const int dwm = use_wt ? kNT : kTN;
   auto TN = [&](float* C, long ldc, int M, int N, const float* dY, long ldy, const float* X, long ldx, int K) {
@@ -601,6 +610,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     p[n++] = TN(g.al_wih + 3 * D, 3 * D + F, 4 * D, F, s.sumG1, 4 * D, s.image_mean, F, B);
     p[n++] = TN(g.cl_x2h_w, LX2, 4 * D, LX2, s.dG2, 4 * D, s.X2, LX2, TB);
     p[n++] = TN(g.cl_h2h_w, D, 4 * D, D, s.dG2, 4 * D, s.h2, D, TB);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm_group(dwm, p, n, st));
   }
   {
@@ -614,6 +624,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     p[n++] = TN(g.ca_sc_w, D, D, D, s.dsc, D, s.ctx_c, D, TB);
     p[n++] = TN(g.ca_tc_w, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.emb_all, D, TB);
     p[n++] = TN(g.ca_tc_w + D, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.X2, LX2, TB);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm_group(dwm, p, n, st));
   }
   {
@@ -625,6 +636,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     const bool dl_plain = (dl.inner == 0 && dl.row_len == nullptr);   // time-major d logits (trainer / rollout)
     if (dl_plain) p[n++] = TN(g.fc_w, D, V, D, dl.p, dl.ld, s.h2drop, D, TB);
     SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm_group(dwm, p, n, st));
     if (dl_plain) {
       SET_PROPAGATE(colsum(dl.p, dl.ld, TB, V, g.fc_b, 1, st));
@@ -640,18 +652,16 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       SET_PROPAGATE(gemm_group(kTN, q, 2, st));
     }
   }
-  SET_PROPAGATE(colsum(s.dG1, 4 * D, TB, 4 * D, g.al_bih, 1, st));
-  SET_PROPAGATE(colsum(s.dG1, 4 * D, TB, 4 * D, g.al_bhh, 1, st));
-  SET_PROPAGATE(colsum(s.dG2, 4 * D, TB, 4 * D, g.cl_x2h_b, 1, st));
-  SET_PROPAGATE(colsum(s.dG2, 4 * D, TB, 4 * D, g.cl_h2h_b, 1, st));
-  SET_PROPAGATE(colsum(s.dS2, LS2, TB, A, g.ca_dec_b, 1, st));
-  SET_PROPAGATE(colsum(s.dS2 + A, LS2, TB, A, g.va_dec_b, 1, st));
-  SET_PROPAGATE(colsum(s.dS2 + 2 * A, LS2, TB, D, g.ca_gate_b, 1, st));
-  SET_PROPAGATE(colsum(s.dS2 + 2 * A + D, LS2, TB, D, g.ca_tc_b, 1, st));
-  SET_PROPAGATE(colsum(s.dsc, D, TB, D, g.ca_sc_b, 1, st));
-  SET_PROPAGATE(colsum(s.dK, D, TB, D, g.cl_gcn_b, 1, st));
-  SET_PROPAGATE(colsum(s.dK, D, TB, D, g.cl_gcm_b, 1, st));
-  SET_PROPAGATE(colsum(s.datt1c, A, B * P, A, g.ca_feat_b, 1, st));
+  {
+    const ColJob cj[] = {
+        {s.dG1, 4L * D, TB, 4 * D, g.al_bih, 0, 0},        {s.dG1, 4L * D, TB, 4 * D, g.al_bhh, 0, 0},
+        {s.dG2, 4L * D, TB, 4 * D, g.cl_x2h_b, 0, 0},      {s.dG2, 4L * D, TB, 4 * D, g.cl_h2h_b, 0, 0},
+        {s.dS2, (long)LS2, TB, A, g.ca_dec_b, 0, 0},        {s.dS2 + A, (long)LS2, TB, A, g.va_dec_b, 0, 0},
+        {s.dS2 + 2 * A, (long)LS2, TB, D, g.ca_gate_b, 0, 0}, {s.dS2 + 2 * A + D, (long)LS2, TB, D, g.ca_tc_b, 0, 0},
+        {s.dsc, (long)D, TB, D, g.ca_sc_b, 0, 0},           {s.dK, (long)D, TB, D, g.cl_gcn_b, 0, 0},
+        {s.dK, (long)D, TB, D, g.cl_gcm_b, 0, 0},           {s.datt1c, (long)A, B * P, A, g.ca_feat_b, 0, 0}};
+    SET_PROPAGATE(colsum_batch(cj, (int)(sizeof(cj) / sizeof(cj[0])), st));
+  }
   {  // d prev_h also flows through cap_features_att
     GemmProblem p = gemm_problem(B * P, D, s.dprev_h, D);
     dx(p, s.datt1c, A, w.ca_feat_w, s.t_ca_feat, A, D, 0);
@@ -662,6 +672,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   if (c.s.train) {
     const int TBR = T * B * R;
     GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_t, D, TBR);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.datt1, A, TBR, A, g.va_feat_b, 1, st));
     GemmProblem px = gemm_problem(TBR, D, s.dfe_t, D);
@@ -670,6 +681,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     SET_PROPAGATE(vis_dropout_bwd(s.fe_pre, s.dfe_t, s.dfe_pre, dec_len_dev, T, B, R, D, c.seed, st));
   } else {
     GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_pre, D, B * R);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.datt1, A, B * R, A, g.va_feat_b, 1, st));
     GemmProblem px = gemm_problem(B * R, D, s.dfe_pre, D);
@@ -679,6 +691,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   }
   {
     GemmProblem pw = TN(g.va_emb_w, F, D, F, s.dfe_pre, D, feats, F, B * R);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.dfe_pre, D, B * R, D, g.va_emb_b, 1, st));
   }
@@ -686,6 +699,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   SET_PROPAGATE(tanh_bwd_inplace(s.dfh, s.fh, (long)B * D, st));
   {
     GemmProblem pw = TN(g.enc_aff_w, D, D, D, s.dfh, D, s.enc_h + (size_t)P * B * D, D, B);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm(dwm, pw, st));
     SET_PROPAGATE(colsum(s.dfh, D, B, D, g.enc_aff_b, 1, st));
     GemmProblem px = gemm_problem(B, D, s.dh_last, D);
@@ -708,6 +722,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     GemmProblem p[2];
     p[0] = TN(g.enc_x2h_w, D, 4 * D, D, s.denc_g, 4 * D, s.emb_prev, D, P * B);
     p[1] = TN(g.enc_h2h_w, D, 4 * D, D, s.denc_g, 4 * D, s.enc_h, D, P * B);
+    SET_PROPAGATE(flush_tr());
     SET_PROPAGATE(gemm_group(dwm, p, 2, st));
     SET_PROPAGATE(colsum(s.denc_g, 4 * D, P * B, 4 * D, g.enc_x2h_b, 1, st));
     SET_PROPAGATE(colsum(s.denc_g, 4 * D, P * B, 4 * D, g.enc_h2h_b, 1, st));

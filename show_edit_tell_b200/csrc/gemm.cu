@@ -193,24 +193,59 @@ int launch(const GemmGroup& g, int total_tiles, cudaStream_t stream) {
   return SET_OK;
 }
 
-__global__ void colsum_kernel(const float* __restrict__ X, long ld, int M, int N, float* __restrict__ out) {
-  // block: 32 columns x 8 row-lanes; grid.y splits the rows, partials meet in atomics
+// several column sums in one grid; a block = 32 columns x (8 row lanes x 8 rows each) of one job
+__global__ void __launch_bounds__(256) colsum_batch_kernel(const __grid_constant__ ColBatch b) {
   __shared__ float red[8][33];
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (n < N)
-    for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += 8 * gridDim.y) s += X[(long)m * ld + n];
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float t = 0.f;
+  int ji = 0;
+  while (ji + 1 < b.n && (int)blockIdx.x >= b.j[ji + 1].block0) ++ji;
+  const ColJob& J = b.j[ji];
+  const int t = blockIdx.x - J.block0;
+  const int cb = t % J.col_blocks, rb = t / J.col_blocks;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = cb * 32 + tx;
+  const int m0 = rb * 64 + ty;
+  float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-    atomicAdd(out + n, t);
+  for (int k = 0; k < 8; ++k) {
+    const int m = m0 + 8 * k;
+    v[k] = (n < J.N && m < J.M) ? J.X[(long)m * J.ld + n] : 0.f;
+  }
+  float sacc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sacc += v[k];
+  red[ty][tx] = sacc;
+  __syncthreads();
+  if (ty == 0 && n < J.N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][tx];
+    atomicAdd(J.out + n, tot);
   }
 }
 
 }  // namespace
+
+int colsum_batch(const ColJob* jobs, int n, cudaStream_t stream) {
+  int i = 0;
+  while (i < n) {
+    ColBatch b;
+    b.n = 0;
+    int blocks = 0;
+    for (; i < n && b.n < kColMaxJobs; ++i) {
+      if (jobs[i].M <= 0 || jobs[i].N <= 0) continue;
+      ColJob j = jobs[i];
+      j.col_blocks = (j.N + 31) / 32;
+      j.block0 = blocks;
+      blocks += j.col_blocks * ((j.M + 63) / 64);
+      b.j[b.n++] = j;
+    }
+    if (b.n == 0) break;
+    colsum_batch_kernel<<<blocks, 256, 0, stream>>>(b);
+    SET_CHECK_CUDA(cudaGetLastError());
+    set_count_launch(1);
+  }
+  return SET_OK;
+}
 
 int g_backend = 0;              // 0: tensor cores where eligible, 1: CUDA cores only
 int g_pdl = getenv("SET_PDL") ? atoi(getenv("SET_PDL")) : 1;
@@ -271,18 +306,8 @@ int colsum(const float* X, long ld, int M, int N, float* out, int beta, cudaStre
   if (N <= 0) return SET_OK;
   if (!beta) SET_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
   if (M <= 0) return SET_OK;
-  static const bool once = [] {
-    cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return true;
-  }();
-  (void)once;
-  dim3 block(32, 8);
-  int gy = (M + 255) / 256;
-  if (gy > 64) gy = 64;
-  colsum_kernel<<<dim3((N + 31) / 32, gy), block, 0, stream>>>(X, ld, M, N, out);
-  SET_CHECK_CUDA(cudaGetLastError());
-  set_count_launch(1);
-  return SET_OK;
+  const ColJob j{X, ld, M, N, out, 0, 0};
+  return colsum_batch(&j, 1, stream);
 }
 
 }  // namespace set

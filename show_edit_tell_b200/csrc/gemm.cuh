@@ -88,4 +88,10 @@ inline int gemm(int mode, const GemmProblem& p, cudaStream_t stream) { return ge
 // column sums: out[n] (+)= sum_m X[m*ld + n]
 int colsum(const float* X, long ld, int M, int N, float* out, int beta, cudaStream_t stream);
 
+// several accumulating column sums in one launch: out[n] += sum_m X[m*ld + n]
+constexpr int kColMaxJobs = 24;
+struct ColJob { const float* X; long ld; int M, N; float* out; int block0, col_blocks; };
+struct ColBatch { int n; ColJob j[kColMaxJobs]; };
+int colsum_batch(const ColJob* jobs, int n, cudaStream_t stream);
+
 }  // namespace set
