@@ -67,13 +67,28 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const float coef = fminf(max_norm / (total + 1e-6f), 1.0f) * grad_scale;
   if (blockIdx.x == 0 && threadIdx.x == 0) scratch[1] = total;
   const float step = lr / bc1;
-  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
-    const float gv = g[x] * coef;
-    const float mv = b1 * m[x] + (1.f - b1) * gv;
-    const float vv = b2 * v[x] + (1.f - b2) * gv * gv;
-    m[x] = mv;
-    v[x] = vv;
-    p[x] -= step * mv / (sqrtf(vv) / bc2s + eps);
+  auto upd = [&](float gx, float& mx, float& vx, float& px) {
+    const float gv = gx * coef;
+    mx = b1 * mx + (1.f - b1) * gv;
+    vx = b2 * vx + (1.f - b2) * gv * gv;
+    px -= step * mx / (sqrtf(vx) / bc2s + eps);
+  };
+  // 128-bit accesses when the four buffers allow it (they are views of flat, aligned allocations)
+  const bool vec = (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                      reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+  const size_t n4 = vec ? (n >> 2) : 0;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n4; x += (size_t)gridDim.x * blockDim.x) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + x);
+    float4 m4 = reinterpret_cast<float4*>(m)[x], v4 = reinterpret_cast<float4*>(v)[x], p4 = reinterpret_cast<float4*>(p)[x];
+    upd(g4.x, m4.x, v4.x, p4.x); upd(g4.y, m4.y, v4.y, p4.y); upd(g4.z, m4.z, v4.z, p4.z); upd(g4.w, m4.w, v4.w, p4.w);
+    reinterpret_cast<float4*>(m)[x] = m4;
+    reinterpret_cast<float4*>(v)[x] = v4;
+    reinterpret_cast<float4*>(p)[x] = p4;
+  }
+  for (size_t x = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+    float mx = m[x], vx = v[x], px = p[x];
+    upd(g[x], mx, vx, px);
+    m[x] = mx; v[x] = vx; p[x] = px;
   }
 }
 
