@@ -52,7 +52,7 @@ constexpr int kConvWarps = SET_TC_CONV_WARPS;   // hi/lo converters, also the ep
 constexpr int kConvGroups = kConvWarps / 4;     // a group = 4 warps = the 4 TMEM lane quarters; K-block i belongs to
                                                 // group i % kConvGroups, so the groups' latency chains overlap
 constexpr int kGT = 128;                        // threads per converter group
-constexpr int kMaxFusedSplit = 6;               // split-K ways the fused epilogue reduces
+constexpr int kMaxFusedSplit = 8;               // split-K ways the fused epilogue reduces
 constexpr int kThreadsTc = 64 + 32 * kConvWarps;
 
 struct TcParams {
@@ -68,12 +68,15 @@ struct TcParams {
   const float* bias; const float* bias2;
   const float* add; long ldadd; int add_mod;
   int beta, act;
+  int fuse_ok;                     // (host) the problem may take the fused epilogue
   int fused;                       // swap mode: split-K partials meet in a scratch slab; the tile's last CTA reduces,
                                    // adds bias/add/C and applies `epi`
   int nblk, blk_stride;            // P tile = nblk blocks of 128/nblk rows; block j starts at global row
                                    // j * blk_stride + tile * (128 / nblk)   (nblk = 4: the four gates of 32 units)
   float* scratch; int* counters;   // library-owned split-K scratch: one [QN][128] slab and two counters per CTA
   const float* zero16;             // 16 bytes of zeros in global memory (stand-in for absent epilogue operands)
+  int cluster;                     // > 1: the `split_k` CTAs of a tile form a thread-block cluster; partials stay in shared
+                                   // memory and meet through DSMEM (no scratch slab, no atomics, no global fences)
   int coop;                        // 1: every CTA of a tile takes a share of the finish (needs a one-wave grid)
   GemmEpi epi;
   int pre_p, pre_q;                // operand is a constant weight: its first pipeline stages load before pdl_wait()
@@ -162,6 +165,34 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// predicated distributed-shared-memory loads (zero when !on)
+__device__ __forceinline__ float2 dsmem_ld2(uint32_t addr, bool on) {
+  float2 v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "@p ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n\t}"
+      : "=f"(v.x), "=f"(v.y) : "r"(addr), "r"((int)on) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr, bool on) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@p ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "r"((int)on) : "memory");
+  return v;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -470,7 +501,17 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
       int nfin = 1, fin = 0;
       bool finisher = true;
       int* cnt = prm.counters + 2 * (blockIdx.x - ks);
-      if (split > 1) {
+      const bool dsm = prm.cluster > 1;
+      uint32_t peer[kMaxFusedSplit];   // the partners' staged tiles in distributed shared memory
+      if (dsm) {
+        // every thread of every CTA of the cluster (the idle producer / MMA warps included, see below) meets here
+        // once the partial tiles are staged; CTA `ks` then finishes 1/split of the tile out of its partners' shared memory
+        cluster_sync_all();
+#pragma unroll
+        for (int k2 = 0; k2 < kMaxFusedSplit; ++k2) peer[k2] = dsmem_addr(smem_u32(ep), (uint32_t)(k2 < split ? k2 : 0));
+        nfin = split; fin = ks;
+        if (ct == 0) TC_STAMP(10);
+      } else if (split > 1) {
         float* part = prm.scratch + (size_t)blockIdx.x * kSlab;
         for (int e = ct; e < rows * 32; e += kCT) {
           const int q = e >> 5, p4 = (e & 31) * 4;
@@ -512,10 +553,16 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
         struct Pre { float4 v[kMaxFusedSplit]; float4 b1, b2, ad, old; };
         // request the pre-activation of 4 consecutive tile rows p4.. of batch row q (global column n..n+3)
         auto request = [&](Pre& r, int q, int p4, int n) {
-          const float* src = pbase + q * kTileP + p4;
+          if (dsm) {
+            const uint32_t off = (uint32_t)(q * EPW_S + p4) * 4u;
 #pragma unroll
-          for (int k2 = 0; k2 < kMaxFusedSplit; ++k2)
-            r.v[k2] = __ldcg(reinterpret_cast<const float4*>(k2 < split ? src + (size_t)k2 * kSlab : zero4));
+            for (int k2 = 0; k2 < kMaxFusedSplit; ++k2) r.v[k2] = dsmem_ld4(peer[k2] + off, k2 < split);
+          } else {
+            const float* src = pbase + q * kTileP + p4;
+#pragma unroll
+            for (int k2 = 0; k2 < kMaxFusedSplit; ++k2)
+              r.v[k2] = __ldcg(reinterpret_cast<const float4*>(k2 < split ? src + (size_t)k2 * kSlab : zero4));
+          }
           r.b1 = __ldg(reinterpret_cast<const float4*>(prm.bias ? prm.bias + n : zero4));
           r.b2 = __ldg(reinterpret_cast<const float4*>(prm.bias2 ? prm.bias2 + n : zero4));
           r.ad = *reinterpret_cast<const float4*>(prm.add ? prm.add + (long)(q % addq_mod) * prm.ldadd + n : zero4);
@@ -591,9 +638,15 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int n = g * D + unit;
-              const float* src = pbase + q * kTileP + g * 32 + u0;
+              if (dsm) {
+                const uint32_t off = (uint32_t)(q * EPW_S + g * 32 + u0) * 4u;
 #pragma unroll
-              for (int k2 = 0; k2 < kMaxFusedSplit; ++k2) v[g][k2] = ld2(k2 < split ? src + (size_t)k2 * kSlab : zero4);
+                for (int k2 = 0; k2 < kMaxFusedSplit; ++k2) v[g][k2] = dsmem_ld2(peer[k2] + off, k2 < split);
+              } else {
+                const float* src = pbase + q * kTileP + g * 32 + u0;
+#pragma unroll
+                for (int k2 = 0; k2 < kMaxFusedSplit; ++k2) v[g][k2] = ld2(k2 < split ? src + (size_t)k2 * kSlab : zero4);
+              }
               b1[g] = ld2(prm.bias ? prm.bias + n : zero4);
               b2[g] = ld2(prm.bias2 ? prm.bias2 + n : zero4);
               ad[g] = ld2(prm.add ? prm.add + (long)(q % addq_mod) * prm.ldadd + n : zero4);
@@ -634,7 +687,8 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
         }
       }
       if (ct == 0) TC_STAMP(12);
-      if (split > 1 && prm.coop) {
+      if (dsm) cluster_sync_all();   // no CTA leaves (and frees its shared memory) while a partner may still read it
+      if (!dsm && split > 1 && prm.coop) {
         // the last CTA to finish reading the slabs re-arms both counters for the next launch
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory");
         if (ct == 0) {
@@ -696,6 +750,10 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
     }
     }   // !fused
   }
+  if (warp < 2 && prm.fused && prm.cluster > 1) {
+    cluster_sync_all();   // partials staged
+    cluster_sync_all();   // partners done reading
+  }
   if (threadIdx.x == 64) TC_STAMP(7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -717,6 +775,7 @@ bool g_tc_ready = false, g_tc_failed = false;
 // serves every launch of the calling stream; the library is used from one stream at a time.
 constexpr int kScratchSlots = 320;
 int g_sm_count = 0;
+int g_max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [c]: clusters of c CTAs (one CTA per SM) resident at once
 float* g_tc_scratch = nullptr;
 int* g_tc_counters = nullptr;
 std::once_flag g_tc_once;
@@ -748,6 +807,21 @@ void tc_init() {
     ok = ok && cudaGetDevice(&dev) == cudaSuccess &&
          cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
   }
+  for (int c = 2; ok && c <= 8; c <<= 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(c * 64); cfg.blockDim = dim3(kThreadsTc); cfg.dynamicSmemBytes = TcCfg<64>::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm_tc_kernel<64, 1>, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+    g_max_clusters[c] = nc;
+  }
+  if (getenv("SET_TC_VERBOSE"))
+    fprintf(stderr, "libset_b200: %d SMs, resident clusters of 2/4/8 CTAs: %d/%d/%d\n", g_sm_count, g_max_clusters[2],
+            g_max_clusters[4], g_max_clusters[8]);
   if (!ok) {
     cudaGetLastError();
     g_tc_failed = true;
@@ -808,6 +882,7 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   // Plain split-K keeps the fire-and-forget red.global.add epilogue (measured faster than the slab protocol
   // when there is no cell to apply); the slab path is for problems that carry a cell.
   prm.fused = (fuse_ok && op != kEpiNone) ? 1 : 0;
+  prm.fuse_ok = fuse_ok ? 1 : 0;
   prm.nblk = gates4 ? 4 : 1;
   prm.blk_stride = gates4 ? g.epi.D : 0;
   prm.epi = g.epi; prm.epi.op = op;
@@ -895,12 +970,25 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     // a single long-K problem that fills only ~half the machine: three partials over two waves is ~1.5x faster
     if (grp.n == 1 && splits[0] == 1 && splittable[0] && tiles_total * 3 <= 2 * 148 && nkbs[0] >= 96) splits[0] = 3;
   }
+  // A single skinny problem: its split-K partners form a thread-block cluster and reduce through distributed shared
+  // memory (power-of-two cluster sizes; the grid must fit the clusters the device can hold at once).
+  int cluster = 1;
+  {
+    static const int cluster_on = getenv("SET_TC_CLUSTER") ? atoi(getenv("SET_TC_CLUSTER")) : 1;
+    if (cluster_on && grp.n == 1 && grp.p[0].fuse_ok && splittable[0] && tiles_total < 148) {
+      int sp = 8;
+      while (sp > 1 && (tiles_total * sp > 148 || nkbs[0] / sp < 4 || tiles_total > g_max_clusters[sp])) sp >>= 1;
+      if (sp > 1) { cluster = sp; splits[0] = sp; }
+    }
+  }
   int cta = 0;
   for (int k = 0; k < grp.n; ++k) {
     TcParams& prm = grp.p[k];
     const GemmProblem& g = probs[idx[k]];
     const int split = splits[k];
     prm.split_k = split;
+    prm.cluster = cluster;
+    if (cluster > 1) prm.fused = 1;
     if (prm.fused && split == 1 && prm.epi.op == kEpiNone) prm.fused = 0;   // nothing to reduce, nothing to apply
     if (prm.fused && cta + tiles[k] * split > kScratchSlots) {
       // (cannot happen with the one-wave heuristic above; guard the slab indexing anyway)
@@ -937,6 +1025,13 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     small.n = grp.n;
     memcpy(small.cta_start, grp.cta_start, sizeof(small.cta_start));
     memcpy(small.p, grp.p, sizeof(TcParams) * grp.n);
+    if (cluster > 1) {
+      if constexpr (G == 1) {
+        if (QN == 64)
+          return launch_chain_cluster(gemm_tc_kernel<64, 1>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, cluster, small);
+        return launch_chain_cluster(gemm_tc_kernel<128, 1>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, cluster, small);
+      }
+    }
     if (QN == 64) return launch_chain(gemm_tc_kernel<64, G>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, small);
     // many tiles per SM and no fused epilogue in play: two CTAs per SM (see TcCfg)
     static const int twin_on = getenv("SET_TC_TWIN") ? atoi(getenv("SET_TC_TWIN")) : 1;
