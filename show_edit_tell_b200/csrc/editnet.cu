@@ -500,10 +500,15 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       GemmProblem p = gemm_problem(b, LX2, dX2t, LX2);      // d[h1 | att_cap | att_img]
       dx(p, dG2t, 4 * D, w.cl_x2h_w, s.t_cl_x2h, 4 * D, LX2, 0);
       p.c_zeroed = c.fresh;
+      int fused = 0;   // the context-gate backward rides on the d att_cap columns of this GEMM's output
+      p.epi.op = kEpiCtxGateBwd; p.epi.D = D; p.epi.col0 = D; p.epi.x0 = s.zst + tb * 3 * D;
+      p.epi.y0 = dS2t + 2 * A; p.epi.y1 = dS2t + 2 * A + D; p.epi.ldy = LS2; p.epi.y2 = s.dsc + tb * D;
+      p.epi_done = &fused;
       SET_PROPAGATE(gemm(dxm, p, st));
+      if (!fused)
+        SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, dX2t + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
+                                   s.dsc + tb * D, b, D, st));
     }
-    SET_PROPAGATE(ctx_gate_bwd(s.zst + tb * 3 * D, dX2t + D, LX2, dS2t + 2 * A, dS2t + 2 * A + D, LS2,
-                               s.dsc + tb * D, b, D, st));
     {
       GemmProblem p = gemm_problem(b, D, dctxt, D);
       p.c_zeroed = c.fresh;
@@ -533,10 +538,15 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       dx(p, dS2t + 2 * A, LS2, w.ca_gate_w, s.t_ca_gate, D, 3 * D, D);
       dx(p, dS2t + 2 * A + D, LS2, w.ca_tc_w, s.t_ca_tc, D, 2 * D, D);
       p.beta = 1;
+      int fused = 0;   // attention-LSTM backward in the epilogue (d h1 is complete once this GEMM has added its terms)
+      p.epi.op = kEpiLstmBwd; p.epi.D = D; p.epi.gates = s.gates1 + tb * 4 * D; p.epi.ld_gates = 4 * D;
+      p.epi.c_prev = s.c1 + tb * D; p.epi.x1 = s.c1 + (tb + B) * D; p.epi.x0 = dh1c_t; p.epi.y0 = s.dc1c; p.epi.y1 = dG1t;
+      p.epi_done = &fused;
       SET_PROPAGATE(gemm(dxm, p, st));
+      if (!fused)
+        SET_PROPAGATE(lstm_bwd(s.gates1 + tb * 4 * D, s.c1 + tb * D, s.c1 + (tb + B) * D, dX2t, LX2, dh1c_t, s.dc1c,
+                               dG1t, b, D, st));
     }
-    SET_PROPAGATE(lstm_bwd(s.gates1 + tb * 4 * D, s.c1 + tb * D, s.c1 + (tb + B) * D, dX2t, LX2, dh1c_t, s.dc1c,
-                           dG1t, b, D, st));
     if (t > 0) {
       GemmProblem p[2];
       p[0] = gemm_problem(b, D, dh1c_t - (size_t)B * D, D); dx(p[0], dG1t, 4 * D, w.al_whh, s.t_al_whh, 4 * D, D, 0);

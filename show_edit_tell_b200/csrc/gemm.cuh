@@ -23,7 +23,7 @@ struct GemmSeg {
 // Pointwise cell fused behind a skinny (M = batch) GEMM: the CTA that completes a tile's split-K reduction
 // applies it to the finished pre-activations (gemm_tc.cu "fused epilogue").  A 4-gate op makes the kernel
 // compose each 128-row weight tile from the 32-row blocks of the four gates of the same 32 hidden units.
-enum GemmEpiOp { kEpiNone = 0, kEpiLstm = 1, kEpiCopy1 = 2, kEpiCopy2 = 3 };
+enum GemmEpiOp { kEpiNone = 0, kEpiLstm = 1, kEpiCopy1 = 2, kEpiCopy2 = 3, kEpiLstmBwd = 4, kEpiCtxGateBwd = 5 };
 struct GemmEpi {
   int op;
   int D;                        // hidden size = gate stride along N
@@ -34,6 +34,13 @@ struct GemmEpi {
   const float* sel; const float* cnew;   // copy2
   float* kgate; float* h2drop;           // copy2
   int train; unsigned long long seed; long drop_base;
+  // reverse-pass cells (elementwise on the GEMM's output columns):
+  //   lstm_bwd:     C = d h (this step's consumers); x0 = carried d h (may be null), x1 = c_cur, c_prev, gates;
+  //                 y0 = d c carry (in/out), y1 = d gates out [rows][4D]
+  //   ctx_gate_bwd: columns [col0, col0 + D) of C are d att_cap; x0 = zst [rows][3D]; y0 = d z-pre, y1 = d tc-pre
+  //                 (row stride ldy), y2 = d sc-pre [rows][D]
+  const float* x0; const float* x1;
+  float* y0; float* y1; float* y2; long ldy; int col0;
 };
 
 struct GemmProblem {

@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
           add4(acc, r.b1); add4(acc, r.b2); add4(acc, r.ad); add4(acc, r.old);
           return acc;
         };
-        if (eo.op == kEpiNone || eo.op == kEpiCopy2) {
+        if (eo.op == kEpiNone || eo.op == kEpiCopy2 || eo.op == kEpiLstmBwd || eo.op == kEpiCtxGateBwd) {
           const int items = rows * 32;   // (q, 4 consecutive rows of the tile)
           const int i0 = (int)((long)items * fin / nfin), i1 = (int)((long)items * (fin + 1) / nfin);
           const int D = eo.D;
@@ -597,9 +597,63 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
               cn = *reinterpret_cast<const float4*>(eo.cnew + x);
               og = *reinterpret_cast<const float4*>(eo.gates + (long)q * eo.ld_gates + 3 * D + n);
             }
+            // reverse-pass cells: their own operands join the same batch of loads
+            float4 r0, r1, r2, r3, r4, r5, r6;
+            const bool cg = (eo.op == kEpiCtxGateBwd) && n >= eo.col0 && n < eo.col0 + D;   // CTA-uniform (tile-aligned range)
+            if (eo.op == kEpiLstmBwd) {
+              const float* gt4 = eo.gates + (long)q * eo.ld_gates + n;
+              r0 = *reinterpret_cast<const float4*>(gt4); r1 = *reinterpret_cast<const float4*>(gt4 + D);
+              r2 = *reinterpret_cast<const float4*>(gt4 + 2 * D); r3 = *reinterpret_cast<const float4*>(gt4 + 3 * D);
+              r4 = *reinterpret_cast<const float4*>(eo.c_prev + x);
+              r5 = *reinterpret_cast<const float4*>(eo.x1 + x);
+              r6 = *reinterpret_cast<const float4*>(eo.y0 + x);
+            } else if (cg) {
+              const float* z4 = eo.x0 + (long)q * 3 * D + (n - eo.col0);
+              r0 = *reinterpret_cast<const float4*>(z4); r1 = *reinterpret_cast<const float4*>(z4 + D);
+              r2 = *reinterpret_cast<const float4*>(z4 + 2 * D);
+            }
+            const float4 dhb = (eo.op == kEpiLstmBwd) ? *reinterpret_cast<const float4*>(eo.x0 ? eo.x0 + x : zero4)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 v = resolve(pr, q, p4);
             if (eo.op == kEpiNone) {
               *reinterpret_cast<float4*>(prm.C + (long)q * prm.ldc + n) = v;
+            } else if (eo.op == kEpiLstmBwd) {
+              // lstm_bwd_core (cells.cu) on 4 units: gates r0..r3 = i,f,g,o; r4 = c_prev, r5 = c_cur, r6 = d c carry
+              float4 di, df, dg, dgo, dcp;
+              auto cell = [](float gi, float gf, float gg, float go, float cp, float cc, float dh, float dcin, float& a, float& b,
+                             float& c, float& d, float& e) {
+                const float tc = tanhf(cc);
+                const float dc = dcin + dh * go * (1.f - tc * tc);
+                a = dc * gg * gi * (1.f - gi);
+                b = dc * cp * gf * (1.f - gf);
+                c = dc * gi * (1.f - gg * gg);
+                d = dh * tc * go * (1.f - go);
+                e = dc * gf;
+              };
+              cell(r0.x, r1.x, r2.x, r3.x, r4.x, r5.x, v.x + dhb.x, r6.x, di.x, df.x, dg.x, dgo.x, dcp.x);
+              cell(r0.y, r1.y, r2.y, r3.y, r4.y, r5.y, v.y + dhb.y, r6.y, di.y, df.y, dg.y, dgo.y, dcp.y);
+              cell(r0.z, r1.z, r2.z, r3.z, r4.z, r5.z, v.z + dhb.z, r6.z, di.z, df.z, dg.z, dgo.z, dcp.z);
+              cell(r0.w, r1.w, r2.w, r3.w, r4.w, r5.w, v.w + dhb.w, r6.w, di.w, df.w, dg.w, dgo.w, dcp.w);
+              float* dgt = eo.y1 + (long)q * 4 * D + n;
+              *reinterpret_cast<float4*>(dgt) = di; *reinterpret_cast<float4*>(dgt + D) = df;
+              *reinterpret_cast<float4*>(dgt + 2 * D) = dg; *reinterpret_cast<float4*>(dgt + 3 * D) = dgo;
+              *reinterpret_cast<float4*>(eo.y0 + x) = dcp;
+            } else if (eo.op == kEpiCtxGateBwd) {
+              *reinterpret_cast<float4*>(prm.C + (long)q * prm.ldc + n) = v;
+              if (cg) {
+                // ctx_gate_bwd_kernel (cells.cu): r0 = z, r1 = tanh(sc), r2 = tanh(tc); v = d att_cap
+                const int d0 = n - eo.col0;
+                float4 dz, dsc, dtc;
+                dz.x = v.x * (r1.x - r2.x) * r0.x * (1.f - r0.x); dz.y = v.y * (r1.y - r2.y) * r0.y * (1.f - r0.y);
+                dz.z = v.z * (r1.z - r2.z) * r0.z * (1.f - r0.z); dz.w = v.w * (r1.w - r2.w) * r0.w * (1.f - r0.w);
+                dsc.x = v.x * r0.x * (1.f - r1.x * r1.x); dsc.y = v.y * r0.y * (1.f - r1.y * r1.y);
+                dsc.z = v.z * r0.z * (1.f - r1.z * r1.z); dsc.w = v.w * r0.w * (1.f - r1.w * r1.w);
+                dtc.x = v.x * (1.f - r0.x) * (1.f - r2.x * r2.x); dtc.y = v.y * (1.f - r0.y) * (1.f - r2.y * r2.y);
+                dtc.z = v.z * (1.f - r0.z) * (1.f - r2.z * r2.z); dtc.w = v.w * (1.f - r0.w) * (1.f - r2.w * r2.w);
+                *reinterpret_cast<float4*>(eo.y0 + (long)q * eo.ldy + d0) = dz;
+                *reinterpret_cast<float4*>(eo.y1 + (long)q * eo.ldy + d0) = dtc;
+                *reinterpret_cast<float4*>(eo.y2 + (long)q * D + d0) = dsc;
+              }
             } else {
               // copy gate (editnet.py:281-285): k = sigmoid(pre); c2 = k sel + (1-k) c_new; h2 = o tanh(c2)
               float4 k, c, h;
@@ -879,6 +933,8 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   const bool gates4 = (op == kEpiLstm || op == kEpiCopy1);
   if (gates4 && !(g.epi.D % 32 == 0 && g.N == 4 * g.epi.D)) return false;
   if (op == kEpiCopy2 && g.N != g.epi.D) return false;
+  if (op == kEpiLstmBwd && g.N != g.epi.D) return false;
+  if (op == kEpiCtxGateBwd && !(g.epi.col0 % kTileP == 0 && g.epi.D % kTileP == 0 && g.epi.col0 + g.epi.D <= g.N)) return false;
   // Plain split-K keeps the fire-and-forget red.global.add epilogue (measured faster than the slab protocol
   // when there is no cell to apply); the slab path is for problems that carry a cell.
   prm.fused = (fuse_ok && op != kEpiNone) ? 1 : 0;
