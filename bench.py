@@ -344,12 +344,13 @@ def main():
                 "pipeline": "double-buffered H2D on a copy stream overlapped with the previous step; loss read "
                             "back one step behind"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "decode step, forward (launch chain of one timestep: 6 GEMM launches "
-                                               "+ LSTM/attention/gate/copy kernels)",
+        "roofline": {"bound": "hbm", "kernel": "decode step, forward (launch chain of one timestep: 5 tcgen05 GEMM launches with "
+                                               "the LSTM / copy-LSTM cells fused in their cluster epilogues + attention + "
+                                               "context gate; programmatic dependent launch between them)",
                      "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     # DRAM bytes of the 10 launches of one forward step, summed from the committed ncu capture
-                     # profiles/r1_step_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum)
-                     "traffic": 192.3e6, "algorithmic_bytes_per_step": step_bytes(B), "us_per_step": step_us,
+                     # DRAM bytes of the 7 launches of one forward step, summed from the committed ncu capture
+                     # profiles/r1_step_kernels_final.md (dram__bytes_read.sum + dram__bytes_write.sum)
+                     "traffic": 188.8e6, "algorithmic_bytes_per_step": step_bytes(B), "us_per_step": step_us,
                      "bwd_us_per_step": bwd_ms.value / T * 1e3, "peak_source": pk_src},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
