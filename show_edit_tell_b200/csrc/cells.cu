@@ -323,6 +323,18 @@ __global__ void enc_mask_kernel(const float* __restrict__ prev_m, float* __restr
 // (2) every thread requests a whole batch of independent 128-bit loads before it consumes the first one.
 constexpr int kRowBatch = 9;
 
+// Pull [rows x bytes_per_row] (row stride in bytes) towards L2, one 128-byte line per thread and iteration.  The
+// attention kernels call it BEFORE pdl_wait() on operands no in-flight kernel writes (region features, the hoisted
+// score projections, encoder outputs): their HBM latency is then paid while the previous GEMM is still running.
+__device__ __forceinline__ void l2_prefetch_rows(const void* base, long row_stride_bytes, int rows, int bytes_per_row) {
+  const int lines = (bytes_per_row + 127) >> 7;
+  const char* b = reinterpret_cast<const char*>(base);
+  for (int e = threadIdx.x; e < rows * lines; e += blockDim.x) {
+    const int r = e / lines, l = e % lines;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (long)r * row_stride_bytes + (long)l * 128));
+  }
+}
+
 // scores s_j = w . act(att1_j + a2) + bias for the n rows of one sample, into sc[] (shared).  A warp takes up to 3
 // rows at a time and requests every piece of them before using any.
 template <bool kTanh>
@@ -419,12 +431,21 @@ __device__ __forceinline__ void attn_weighted_rows(const float* __restrict__ row
 // dynamic smem: a2[A] | wv[A] | sc[max(P,R) padded] | part[4 * blockDim]
 __global__ void __launch_bounds__(kAttnThreads, 3) attention_fwd_kernel(const AttnFwdArgs a, int cap_slices) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float sm[];
   const int A = a.A;
   const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool cap = ((int)blockIdx.y < cap_slices);
   const int n = cap ? a.P : a.R;
+  {
+    // constant operands of this CTA: its sample's hoisted score projection and its column slice of the values
+    const int slices = cap ? cap_slices : (int)gridDim.y - cap_slices, sl = cap ? (int)blockIdx.y : (int)blockIdx.y - cap_slices;
+    const int width = cap ? a.D : a.F;                       // value row length (floats)
+    const int per4 = ((width >> 2) + slices - 1) / slices;   // float4 columns per slice
+    const float* vals = cap ? a.prev_h + (long)i * a.P * a.D : a.feats + (long)i * a.R * a.F;
+    l2_prefetch_rows(cap ? a.att1c + (long)i * a.P * A : a.att1v + (long)i * a.R * A, (long)A * 4, n, A * 4);
+    l2_prefetch_rows(vals + (long)sl * per4 * 4, (long)width * 4, n, per4 * 16);
+  }
+  pdl_wait();
   float* a2 = sm;
   float* wv = sm + A;
   float* sc = sm + 2 * A;
@@ -495,10 +516,19 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attention_fwd_kernel(const At
 __global__ void __launch_bounds__(kAttnThreads, 3) attention_bwd_dal_kernel(const AttnBwdArgs a, float* __restrict__ dal_out,
                                                                             int cap_slices) {
   pdl_trigger();
-  pdl_wait();
   const bool cap = ((int)blockIdx.y < cap_slices);
   const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   float* dal = dal_out + (long)i * (a.P + a.R);
+  if (cap) {
+    // this CTA's value rows (constant): rows blockIdx.y, + cap_slices, ...
+    const int rows = (a.P - (int)blockIdx.y + cap_slices - 1) / cap_slices;
+    l2_prefetch_rows(a.prev_h + ((long)i * a.P + blockIdx.y) * a.D, (long)cap_slices * a.D * 4, rows, a.D * 4);
+  } else {
+    const int slices = gridDim.y - cap_slices, sl = blockIdx.y - cap_slices;
+    const int rows = (a.R - sl + slices - 1) / slices;
+    l2_prefetch_rows(a.feats + ((long)i * a.R + sl) * a.F, (long)slices * a.F * 4, rows, a.F * 4);
+  }
+  pdl_wait();
   // <x, y_r> for this CTA's rows: a warp per row, 8 x 128-bit loads per lane in flight
   auto dots = [&](const float* __restrict__ x, const float* __restrict__ ybase, long ystride, int len4, int r_first, int r_step,
                   int nrows, int nvalid, float* out, int js, const float* __restrict__ xs, const float* __restrict__ ys) {
@@ -548,11 +578,18 @@ __global__ void __launch_bounds__(kAttnThreads, 3) attention_bwd_dal_kernel(cons
 __global__ void __launch_bounds__(kAttnThreads, 3) attention_bwd_main_kernel(const AttnBwdArgs a, const float* __restrict__ dal_in,
                                                                              int cap_slices) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float sm[];
   const int A = a.A;
   const int y = blockIdx.y;
   const bool cap = (y < cap_slices);
+  {
+    // the unit slice of the hoisted score projection this CTA differentiates (constant)
+    const int slices_ = cap ? cap_slices : (int)gridDim.y - cap_slices, sl_ = cap ? y : y - cap_slices;
+    const int per_ = (A + slices_ - 1) / slices_;
+    const float* att1_ = cap ? a.att1c + (long)blockIdx.x * a.P * A : a.att1v + (long)blockIdx.x * a.R * A;
+    l2_prefetch_rows(att1_ + (long)sl_ * per_, (long)A * 4, cap ? a.P : a.R, per_ * 4);
+  }
+  pdl_wait();
   const int n = cap ? a.P : a.R;
   const int npad = (max(a.P, a.R) + 3) & ~3;
   float* a2 = sm;

@@ -472,6 +472,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     SET_PROPAGATE(gemm(dxm, p, st));
   }
   SET_PROPAGATE(profile_mark(2, st));
+  bool copy2_done = false;
   for (int t = T - 1; t >= 0; --t) {
     const int b = bt_host[t];
     if (b <= 0) continue;
@@ -486,16 +487,24 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     float* dctxt = s.dctx + tb * D;
     float* dh1c_t = s.dh1c + tb * D;
     float* dh2c_t = s.dh2c + tb * D;
-    SET_PROPAGATE(copy2_bwd(dh2c_t, s.dh2raw + tb * D, s.dc2c, g2t, s.c2 + (tb + B) * D, s.kgate + tb * D,
-                            s.sel + tb * D, s.cnew + tb * D, dG2t, dKt, s.dsel, s.dcnew, b, D, c.s.train, c.seed,
-                            (long)tb * D, st));
+    if (!copy2_done)   // else: applied by the epilogue of the previous iteration's last GEMM
+      SET_PROPAGATE(copy2_bwd(dh2c_t, s.dh2raw + tb * D, s.dc2c, g2t, s.c2 + (tb + B) * D, s.kgate + tb * D,
+                              s.sel + tb * D, s.cnew + tb * D, dG2t, dKt, s.dsel, s.dcnew, b, D, c.s.train, c.seed,
+                              (long)tb * D, st));
+    copy2_done = false;
     {
       GemmProblem p[2];
       p[0] = gemm_problem(b, D, s.dcnew, D); dx(p[0], dKt, D, w.cl_gcn_w, s.t_cl_gcn, D, D, 0); p[0].beta = 1;
       p[1] = gemm_problem(b, D, s.dsel, D); dx(p[1], dKt, D, w.cl_gcm_w, s.t_cl_gcm, D, D, 0); p[1].beta = 1;
+      // (optional, off: in a two-problem group the fused cell takes the scratch-slab epilogue, which costs more than the
+      // stand-alone kernel saves -- 110.6 vs 108.5 us per reverse step on B200)
+      int fused = 0;   // copy-LSTM stage-1 backward on the finished d c_new
+      static const int fuse_copy1_bwd = getenv("SET_FUSE_COPY1_BWD") ? atoi(getenv("SET_FUSE_COPY1_BWD")) : 0;
+      if (fuse_copy1_bwd) p[0].epi.op = kEpiCopy1Bwd; p[0].epi.D = D; p[0].epi.gates = const_cast<float*>(g2t); p[0].epi.ld_gates = 4 * D;
+      p[0].epi.c_prev = s.c2 + tb * D; p[0].epi.y0 = s.dc2c; p[0].epi.y1 = dG2t; p[0].epi_done = &fused;
       SET_PROPAGATE(gemm_group(dxm, p, 2, st));
+      if (!fused) SET_PROPAGATE(copy1_bwd(s.dcnew, g2t, s.c2 + tb * D, dG2t, s.dc2c, b, D, st));
     }
-    SET_PROPAGATE(copy1_bwd(s.dcnew, g2t, s.c2 + tb * D, dG2t, s.dc2c, b, D, st));
     {
       GemmProblem p = gemm_problem(b, LX2, dX2t, LX2);      // d[h1 | att_cap | att_img]
       dx(p, dG2t, 4 * D, w.cl_x2h_w, s.t_cl_x2h, 4 * D, LX2, 0);
@@ -554,7 +563,22 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       p[0].c_zeroed = p[1].c_zeroed = c.fresh;
       dx(p[1], dG1t, 4 * D, w.al_wih, s.t_al_wih, 4 * D, 3 * D + F, 2 * D);
       dx(p[1], dG2t, 4 * D, w.cl_h2h_w, s.t_cl_h2h, 4 * D, D, 0);
+      // step t-1 opens with the copy-LSTM stage-2 backward on exactly this GEMM's d h2 carry: it can ride in this
+      // epilogue when the two steps decode the same rows (optional, off: the fused path caps the split of this 50 MB
+      // GEMM and the reverse step gets 12 us slower)
+      int fused = 0;
+      static const int fuse_copy2_bwd = getenv("SET_FUSE_COPY2_BWD") ? atoi(getenv("SET_FUSE_COPY2_BWD")) : 0;
+      if (fuse_copy2_bwd && bt_host[t - 1] == b) {
+        const size_t tp = tb - B;
+        GemmEpi& e = p[1].epi;
+        e.op = kEpiCopy2Bwd; e.D = D; e.x0 = s.dh2raw + tp * D; e.y0 = s.dc2c; e.gates = s.g2 + tp * 4 * D; e.ld_gates = 4 * D;
+        e.x1 = s.c2 + (tp + B) * D; e.kgate = s.kgate + tp * D; e.sel = s.sel + tp * D; e.cnew = s.cnew + tp * D;
+        e.y1 = s.dG2 + tp * 4 * D; e.y2 = s.dK + tp * D; e.x2 = s.dsel; e.x3 = s.dcnew;
+        e.train = c.s.train; e.seed = c.seed; e.drop_base = (long)tp * D;
+        p[1].epi_done = &fused;
+      }
       SET_PROPAGATE(gemm_group(dxm, p, 2, st));
+      copy2_done = fused != 0;
     }
   }
   SET_PROPAGATE(profile_mark(3, st));

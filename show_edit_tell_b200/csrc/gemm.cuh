@@ -23,7 +23,7 @@ struct GemmSeg {
 // Pointwise cell fused behind a skinny (M = batch) GEMM: the CTA that completes a tile's split-K reduction
 // applies it to the finished pre-activations (gemm_tc.cu "fused epilogue").  A 4-gate op makes the kernel
 // compose each 128-row weight tile from the 32-row blocks of the four gates of the same 32 hidden units.
-enum GemmEpiOp { kEpiNone = 0, kEpiLstm = 1, kEpiCopy1 = 2, kEpiCopy2 = 3, kEpiLstmBwd = 4, kEpiCtxGateBwd = 5 };
+enum GemmEpiOp { kEpiNone = 0, kEpiLstm = 1, kEpiCopy1 = 2, kEpiCopy2 = 3, kEpiLstmBwd = 4, kEpiCtxGateBwd = 5, kEpiCopy1Bwd = 6, kEpiCopy2Bwd = 7 };
 struct GemmEpi {
   int op;
   int D;                        // hidden size = gate stride along N
@@ -39,8 +39,12 @@ struct GemmEpi {
   //                 y0 = d c carry (in/out), y1 = d gates out [rows][4D]
   //   ctx_gate_bwd: columns [col0, col0 + D) of C are d att_cap; x0 = zst [rows][3D]; y0 = d z-pre, y1 = d tc-pre
   //                 (row stride ldy), y2 = d sc-pre [rows][D]
+  //   copy1_bwd:    C = d c_new; gates = g2 (i,f,g read), c_prev = c2_prev; y0 = d c2 carry (written), y1 = d g2 [rows][4D]
+  //   copy2_bwd:    C = carried d h2; x0 = d dropout(h2) raw (may be null), y0 = d c2 carry (read), gates = g2 (o read),
+  //                 x1 = c2, kgate (read), sel, cnew; y1 = d g2 (o gate written), y2 = d k-pre, x2 = d sel out, x3 = d c_new out
   const float* x0; const float* x1;
   float* y0; float* y1; float* y2; long ldy; int col0;
+  float* x2; float* x3;
 };
 
 struct GemmProblem {

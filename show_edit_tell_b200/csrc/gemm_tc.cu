@@ -223,8 +223,17 @@ struct TcCfg {
 #define SET_TC_NQ64 6
 #define SET_TC_NP64 6
 #endif
-  static constexpr int kNQ = TWIN ? 2 : ((QN <= 64) ? SET_TC_NQ64 : 3);
-  static constexpr int kNP = TWIN ? 3 : ((QN <= 64) ? SET_TC_NP64 : 6);
+  static constexpr int kNQ = TWIN ? 2 : ((QN <= 64) ? SET_TC_NQ64 : 4);
+  static constexpr int kNP = TWIN ? 3 : ((QN <= 64) ? SET_TC_NP64 : 4);
+  // Converter groups take alternate K-blocks and wait on q_full by PARITY, which only tells a phase from its
+  // predecessor: a group must therefore visit every slot on consecutive phases, i.e. kNQ % groups == 0.  (With 3 Q
+  // slots and 2 groups a group came back to a slot two phases later; TMA completes out of order, so the phase in
+  // between could still be pending and the wait returned at once on stale data -- a 1-in-3000 corruption of whole
+  // output tiles, found with tools/stress_repeat.py.)  The P ring needs no such rule: a group reaches the P wait of
+  // K-block i only after Q(i) landed, which the producer issues after the MMA of K-block i - kNQ, i.e. after every
+  // earlier P tile was consumed.
+  static_assert(kNQ % kConvGroups == 0, "a converter group must revisit a Q slot on consecutive barrier phases");
+  static_assert(kNP >= kNQ, "the producer refills P slot (j - kNQ + kNP) % kNP behind the MMA of K-block j - kNQ");
   static constexpr uint32_t kTmemCols = TWIN ? 256u : 512u;
   static_assert(!TWIN || QN == 128, "the twin configuration is built for 128-wide Q tiles");
   static constexpr int kPBytes = kTileP * 128;
@@ -400,6 +409,9 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
         lo = x - hi;
       };
       // Q: hi written back in place over the TMA'd tile, lo to the sibling tile
+      // (A parity wait only tells phase n from phase n-1, so a waiter must see EVERY phase of a barrier.  The groups
+      // alternate K-blocks: kNQ is a multiple of the group count, hence a group revisits a Q slot on consecutive
+      // phases -- see the static_assert in TcCfg.  The P wait below is gated by this one.)
       mbar_wait(q_full(sq), (uint32_t)(i / NQ) & 1u);
       if (gt == 0) KB_STAMP(i, 2);
       float4* q_hi = reinterpret_cast<float4*>(gen_base + (q_base - base) + sq * Cfg::kQSlot);
@@ -580,7 +592,7 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
           add4(acc, r.b1); add4(acc, r.b2); add4(acc, r.ad); add4(acc, r.old);
           return acc;
         };
-        if (eo.op == kEpiNone || eo.op == kEpiCopy2 || eo.op == kEpiLstmBwd || eo.op == kEpiCtxGateBwd) {
+        if (eo.op != kEpiLstm && eo.op != kEpiCopy1) {
           const int items = rows * 32;   // (q, 4 consecutive rows of the tile)
           const int i0 = (int)((long)items * fin / nfin), i1 = (int)((long)items * (fin + 1) / nfin);
           const int D = eo.D;
@@ -612,6 +624,20 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
               r0 = *reinterpret_cast<const float4*>(z4); r1 = *reinterpret_cast<const float4*>(z4 + D);
               r2 = *reinterpret_cast<const float4*>(z4 + 2 * D);
             }
+            else if (eo.op == kEpiCopy1Bwd) {
+              const float* gt4 = eo.gates + (long)q * eo.ld_gates + n;
+              r0 = *reinterpret_cast<const float4*>(gt4); r1 = *reinterpret_cast<const float4*>(gt4 + D);
+              r2 = *reinterpret_cast<const float4*>(gt4 + 2 * D);
+              r4 = *reinterpret_cast<const float4*>(eo.c_prev + x);
+            } else if (eo.op == kEpiCopy2Bwd) {
+              r0 = *reinterpret_cast<const float4*>(eo.gates + (long)q * eo.ld_gates + 3 * D + n);   // o gate
+              r1 = *reinterpret_cast<const float4*>(eo.x1 + x);      // c2
+              r2 = *reinterpret_cast<const float4*>(eo.kgate + x);
+              r3 = *reinterpret_cast<const float4*>(eo.sel + x);
+              r4 = *reinterpret_cast<const float4*>(eo.cnew + x);
+              r5 = *reinterpret_cast<const float4*>(eo.y0 + x);      // d c2 carry
+              r6 = *reinterpret_cast<const float4*>(eo.x0 ? eo.x0 + x : zero4);   // d dropout(h2), raw
+            }
             const float4 dhb = (eo.op == kEpiLstmBwd) ? *reinterpret_cast<const float4*>(eo.x0 ? eo.x0 + x : zero4)
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 v = resolve(pr, q, p4);
@@ -638,6 +664,46 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
               *reinterpret_cast<float4*>(dgt) = di; *reinterpret_cast<float4*>(dgt + D) = df;
               *reinterpret_cast<float4*>(dgt + 2 * D) = dg; *reinterpret_cast<float4*>(dgt + 3 * D) = dgo;
               *reinterpret_cast<float4*>(eo.y0 + x) = dcp;
+            } else if (eo.op == kEpiCopy1Bwd) {
+              // copy1_bwd_kernel (cells.cu): v = d c_new; r0,r1,r2 = i,f,g; r4 = c2_prev
+              float4 di, df, dg, dcp;
+              di.x = v.x * r2.x * r0.x * (1.f - r0.x); di.y = v.y * r2.y * r0.y * (1.f - r0.y);
+              di.z = v.z * r2.z * r0.z * (1.f - r0.z); di.w = v.w * r2.w * r0.w * (1.f - r0.w);
+              df.x = v.x * r4.x * r1.x * (1.f - r1.x); df.y = v.y * r4.y * r1.y * (1.f - r1.y);
+              df.z = v.z * r4.z * r1.z * (1.f - r1.z); df.w = v.w * r4.w * r1.w * (1.f - r1.w);
+              dg.x = v.x * r0.x * (1.f - r2.x * r2.x); dg.y = v.y * r0.y * (1.f - r2.y * r2.y);
+              dg.z = v.z * r0.z * (1.f - r2.z * r2.z); dg.w = v.w * r0.w * (1.f - r2.w * r2.w);
+              dcp.x = v.x * r1.x; dcp.y = v.y * r1.y; dcp.z = v.z * r1.z; dcp.w = v.w * r1.w;
+              float* dgt = eo.y1 + (long)q * 4 * D + n;
+              *reinterpret_cast<float4*>(dgt) = di; *reinterpret_cast<float4*>(dgt + D) = df;
+              *reinterpret_cast<float4*>(dgt + 2 * D) = dg;
+              *reinterpret_cast<float4*>(eo.y0 + x) = dcp;
+            } else if (eo.op == kEpiCopy2Bwd) {
+              // copy2_bwd_kernel (cells.cu): v = carried d h2; r0 = o, r1 = c2, r2 = k, r3 = sel, r4 = c_new, r5 = d c2 carry
+              float4 dfc = r6;
+              if (eo.train && eo.x0) {
+                const uint32_t keep = drop_keep4(eo.seed, kSiteFc, (uint64_t)(eo.drop_base + x));
+                dfc.x = (keep & 1u) ? dfc.x * 2.f : 0.f; dfc.y = (keep & 2u) ? dfc.y * 2.f : 0.f;
+                dfc.z = (keep & 4u) ? dfc.z * 2.f : 0.f; dfc.w = (keep & 8u) ? dfc.w * 2.f : 0.f;
+              }
+              float4 dgo, dk, dsl, dcn;
+              auto cell = [](float dh, float go, float c2v, float k, float sl, float cn, float dcin, float& a, float& b, float& c,
+                             float& d) {
+                const float tc = tanhf(c2v);
+                a = dh * tc * go * (1.f - go);
+                const float dc = dcin + dh * go * (1.f - tc * tc);
+                b = dc * (sl - cn) * k * (1.f - k);
+                c = dc * k;
+                d = dc * (1.f - k);
+              };
+              cell(v.x + dfc.x, r0.x, r1.x, r2.x, r3.x, r4.x, r5.x, dgo.x, dk.x, dsl.x, dcn.x);
+              cell(v.y + dfc.y, r0.y, r1.y, r2.y, r3.y, r4.y, r5.y, dgo.y, dk.y, dsl.y, dcn.y);
+              cell(v.z + dfc.z, r0.z, r1.z, r2.z, r3.z, r4.z, r5.z, dgo.z, dk.z, dsl.z, dcn.z);
+              cell(v.w + dfc.w, r0.w, r1.w, r2.w, r3.w, r4.w, r5.w, dgo.w, dk.w, dsl.w, dcn.w);
+              *reinterpret_cast<float4*>(eo.y1 + (long)q * 4 * D + 3 * D + n) = dgo;
+              *reinterpret_cast<float4*>(eo.y2 + x) = dk;
+              *reinterpret_cast<float4*>(eo.x2 + x) = dsl;
+              *reinterpret_cast<float4*>(eo.x3 + x) = dcn;
             } else if (eo.op == kEpiCtxGateBwd) {
               *reinterpret_cast<float4*>(prm.C + (long)q * prm.ldc + n) = v;
               if (cg) {
@@ -933,11 +999,14 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   const bool gates4 = (op == kEpiLstm || op == kEpiCopy1);
   if (gates4 && !(g.epi.D % 32 == 0 && g.N == 4 * g.epi.D)) return false;
   if (op == kEpiCopy2 && g.N != g.epi.D) return false;
-  if (op == kEpiLstmBwd && g.N != g.epi.D) return false;
+  if ((op == kEpiLstmBwd || op == kEpiCopy1Bwd || op == kEpiCopy2Bwd) && g.N != g.epi.D) return false;
   if (op == kEpiCtxGateBwd && !(g.epi.col0 % kTileP == 0 && g.epi.D % kTileP == 0 && g.epi.col0 + g.epi.D <= g.N)) return false;
   // Plain split-K keeps the fire-and-forget red.global.add epilogue (measured faster than the slab protocol
   // when there is no cell to apply); the slab path is for problems that carry a cell.
-  prm.fused = (fuse_ok && op != kEpiNone) ? 1 : 0;
+  // ... and for plain problems whose C is neither pre-zeroed nor accumulated into: the slab path needs no memset
+  // in front of the launch (SET_TC_PLAIN_FUSED=0 restores memset + red.global.add for them).
+  static const int plain_fused = getenv("SET_TC_PLAIN_FUSED") ? atoi(getenv("SET_TC_PLAIN_FUSED")) : 1;
+  prm.fused = (fuse_ok && (op != kEpiNone || (plain_fused && !g.beta && !g.c_zeroed))) ? 1 : 0;
   prm.fuse_ok = fuse_ok ? 1 : 0;
   prm.nblk = gates4 ? 4 : 1;
   prm.blk_stride = gates4 ? g.epi.D : 0;
@@ -1031,10 +1100,30 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
   int cluster = 1;
   {
     static const int cluster_on = getenv("SET_TC_CLUSTER") ? atoi(getenv("SET_TC_CLUSTER")) : 1;
-    if (cluster_on && grp.n == 1 && grp.p[0].fuse_ok && splittable[0] && tiles_total < 148) {
-      int sp = 8;
-      while (sp > 1 && (tiles_total * sp > 148 || nkbs[0] / sp < 4 || tiles_total > g_max_clusters[sp])) sp >>= 1;
-      if (sp > 1) { cluster = sp; splits[0] = sp; }
+    bool all_ok = cluster_on && tiles_total < 148;
+    long min_nkb = 1L << 40, max_nkb = 0;
+    double greedy_max = 0.0;
+    for (int k = 0; k < grp.n; ++k) {
+      all_ok = all_ok && grp.p[k].fuse_ok && splittable[k];
+      min_nkb = nkbs[k] < min_nkb ? nkbs[k] : min_nkb;
+      max_nkb = nkbs[k] > max_nkb ? nkbs[k] : max_nkb;
+      const double l = (double)nkbs[k] / splits[k];
+      greedy_max = l > greedy_max ? l : greedy_max;
+    }
+    if (all_ok) {
+      // one split for the whole launch (= the cluster size).  Groups: off by default (measured on B200: the three-GEMM
+      // group on ctx/sel and the reverse-pass pairs run 2-3 us SLOWER as clusters than with per-problem splits +
+      // red.global.add -- uniform splits unbalance them and big clusters wait for whole GPC slices to drain); when
+      // enabled (SET_TC_GROUP_CLUSTER=1), only if it does not cost more than ~12
+      // K-blocks of load balance against the greedy plan (the cluster epilogue is worth about that much)
+      static const int max_cluster = getenv("SET_TC_MAX_CLUSTER") ? atoi(getenv("SET_TC_MAX_CLUSTER")) : 8;
+      static const int group_cluster = getenv("SET_TC_GROUP_CLUSTER") ? atoi(getenv("SET_TC_GROUP_CLUSTER")) : 0;
+      int sp = max_cluster >= 8 ? 8 : (max_cluster >= 4 ? 4 : (max_cluster >= 2 ? 2 : 1));
+      while (sp > 1 && (tiles_total * sp > 148 || min_nkb / sp < 4 || tiles_total > g_max_clusters[sp])) sp >>= 1;
+      if (sp > 1 && (grp.n == 1 || (group_cluster && (double)max_nkb / sp <= greedy_max + 12.0))) {
+        cluster = sp;
+        for (int k = 0; k < grp.n; ++k) splits[k] = sp;
+      }
     }
   }
   int cta = 0;
@@ -1082,11 +1171,9 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     memcpy(small.cta_start, grp.cta_start, sizeof(small.cta_start));
     memcpy(small.p, grp.p, sizeof(TcParams) * grp.n);
     if (cluster > 1) {
-      if constexpr (G == 1) {
-        if (QN == 64)
-          return launch_chain_cluster(gemm_tc_kernel<64, 1>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, cluster, small);
-        return launch_chain_cluster(gemm_tc_kernel<128, 1>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, cluster, small);
-      }
+      if (QN == 64)
+        return launch_chain_cluster(gemm_tc_kernel<64, G>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, cluster, small);
+      return launch_chain_cluster(gemm_tc_kernel<128, G>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, cluster, small);
     }
     if (QN == 64) return launch_chain(gemm_tc_kernel<64, G>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, small);
     // many tiles per SM and no fused epilogue in play: two CTAs per SM (see TcCfg)
