@@ -224,11 +224,18 @@ int encode_prev(Ctx& c, const int64_t* prev, const int64_t* prev_len) {
     GemmProblem p = gemm_problem(B, 4 * D, pre, 4 * D);
     if (t > 0) gemm_add_seg(p, s.enc_h + (size_t)t * B * D, D, w.enc_h2h_w, D, D);
     p.add = s.enc_xg + (size_t)t * B * 4 * D; p.ldadd = 4 * D; p.c_zeroed = c.fresh; p.w_const = 1;
+    int fused = 0;   // the length-masked encoder cell in the GEMM's epilogue
+    p.epi.op = kEpiLstm; p.epi.D = D; p.epi.c_prev = s.enc_c + (size_t)t * B * D; p.epi.c_out = s.enc_c + (size_t)(t + 1) * B * D;
+    p.epi.h_out = s.enc_h + (size_t)(t + 1) * B * D; p.epi.ld_h = D; p.epi.gates = pre; p.epi.ld_gates = 4 * D;
+    p.epi.len = reinterpret_cast<const long long*>(prev_len); p.epi.t = t; p.epi.h_prev = s.enc_h + (size_t)t * B * D;
+    p.epi.seq_h = s.prev_h; p.epi.seq_m = s.prev_m; p.epi.seq_ld = (long)P * D;
+    p.epi_done = &fused;
     SET_PROPAGATE(gemm(kNT, p, st));
-    SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
-                           s.enc_gates + (size_t)t * B * 4 * D, s.enc_c + (size_t)(t + 1) * B * D,
-                           s.enc_h + (size_t)(t + 1) * B * D, D, B, D, prev_len, t, s.prev_h, s.prev_m,
-                           (long)P * D, st));
+    if (!fused)
+      SET_PROPAGATE(lstm_fwd(pre, 4 * D, s.enc_c + (size_t)t * B * D, s.enc_h + (size_t)t * B * D,
+                             s.enc_gates + (size_t)t * B * 4 * D, s.enc_c + (size_t)(t + 1) * B * D,
+                             s.enc_h + (size_t)(t + 1) * B * D, D, B, D, prev_len, t, s.prev_h, s.prev_m,
+                             (long)P * D, st));
   }
   SET_PROPAGATE(enc_mask(s.prev_m, s.mask, B, P, D, st));
   {

@@ -45,6 +45,9 @@ struct GemmEpi {
   const float* x0; const float* x1;
   float* y0; float* y1; float* y2; long ldy; int col0;
   float* x2; float* x3;
+  // length-masked LSTM (the previous-caption encoder, editnet.py:333-338): row i is active at step t iff len[i] > t;
+  // inactive rows carry c/h through and store zero gates; seq_h/seq_m (optional) get h/c of active rows, else 0
+  const long long* len; int t; const float* h_prev; float* seq_h; float* seq_m; long seq_ld;
 };
 
 struct GemmProblem {

@@ -794,14 +794,25 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
             gg.x = tanhf(pre[2].x); gg.y = tanhf(pre[2].y);
             go.x = sigmoidf_(pre[3].x); go.y = sigmoidf_(pre[3].y);
             c.x = gf.x * cp.x + gi.x * gg.x; c.y = gf.y * cp.y + gi.y * gg.y;
+            const bool active = (eo.len == nullptr) || (eo.len[q] > (long long)eo.t);
+            if (!active) {   // carried through unchanged; zero gates (lstm_fwd_kernel, cells.cu)
+              gi = gf = gg = go = make_float2(0.f, 0.f);
+              c = cp;
+            }
             float* g = eo.gates + (long)q * eo.ld_gates + unit;
             *reinterpret_cast<float2*>(g) = gi; *reinterpret_cast<float2*>(g + D) = gf;
             *reinterpret_cast<float2*>(g + 2 * D) = gg; *reinterpret_cast<float2*>(g + 3 * D) = go;
             *reinterpret_cast<float2*>(eo.c_out + (long)q * D + unit) = c;
             if (eo.op == kEpiLstm) {
               float2 h;
-              h.x = go.x * tanhf(c.x); h.y = go.y * tanhf(c.y);
+              if (active) { h.x = go.x * tanhf(c.x); h.y = go.y * tanhf(c.y); }
+              else h = ld2(eo.h_prev + (long)q * D + unit);
               *reinterpret_cast<float2*>(eo.h_out + (long)q * eo.ld_h + unit) = h;
+              if (eo.seq_h) {
+                const long so = (long)q * eo.seq_ld + (long)eo.t * D + unit;
+                *reinterpret_cast<float2*>(eo.seq_h + so) = active ? h : make_float2(0.f, 0.f);
+                *reinterpret_cast<float2*>(eo.seq_m + so) = active ? c : make_float2(0.f, 0.f);
+              }
             }
           }
         }
