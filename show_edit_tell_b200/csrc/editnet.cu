@@ -747,16 +747,29 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     dx(px, s.dfh, D, w.enc_aff_w, s.t_enc_aff, D, D, 0);
     SET_PROPAGATE(gemm(dxm, px, st));
   }
+  bool enc_cell_done = false;   // step t's cell already applied by the epilogue of the previous iteration's GEMM
   for (int t = P - 1; t >= 0; --t) {
     const size_t tb = (size_t)t * B;
-    SET_PROPAGATE(enc_lstm_bwd(s.enc_gates + tb * 4 * D, s.enc_c + tb * D, s.enc_c + (tb + B) * D, s.dh_run + tb * D,
-                               s.dc_run, s.dprev_h, s.dprev_m, (long)P * D, s.dh_last, prev_len, t,
-                               s.denc_g + tb * 4 * D, B, D, st));
+    if (!enc_cell_done)
+      SET_PROPAGATE(enc_lstm_bwd(s.enc_gates + tb * 4 * D, s.enc_c + tb * D, s.enc_c + (tb + B) * D, s.dh_run + tb * D,
+                                 s.dc_run, s.dprev_h, s.dprev_m, (long)P * D, s.dh_last, prev_len, t,
+                                 s.denc_g + tb * 4 * D, B, D, st));
+    enc_cell_done = false;
     if (t > 0) {
       GemmProblem p = gemm_problem(B, D, s.dh_run + (tb - B) * D, D);
       p.c_zeroed = c.fresh;
       dx(p, s.denc_g + tb * 4 * D, 4 * D, w.enc_h2h_w, s.t_enc_h2h, 4 * D, D, 0);
+      // this GEMM's output is the d h that step t-1's cell backward starts from: apply that cell in the epilogue
+      int fused = 0;
+      const size_t tp = tb - B;
+      GemmEpi& e = p.epi;
+      e.op = kEpiLstmBwd; e.D = D; e.gates = s.enc_gates + tp * 4 * D; e.ld_gates = 4 * D; e.c_prev = s.enc_c + tp * D;
+      e.x1 = s.enc_c + (tp + B) * D; e.x0 = nullptr; e.y0 = s.dc_run; e.y1 = s.denc_g + tp * 4 * D;
+      e.len = reinterpret_cast<const long long*>(prev_len); e.t = t - 1; e.seq_h = s.dprev_h; e.seq_m = s.dprev_m;
+      e.seq_ld = (long)P * D; e.h_prev = s.dh_last;
+      p.epi_done = &fused;
       SET_PROPAGATE(gemm(dxm, p, st));
+      enc_cell_done = fused != 0;
     }
   }
   {

@@ -638,8 +638,20 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
               r5 = *reinterpret_cast<const float4*>(eo.y0 + x);      // d c2 carry
               r6 = *reinterpret_cast<const float4*>(eo.x0 ? eo.x0 + x : zero4);   // d dropout(h2), raw
             }
-            const float4 dhb = (eo.op == kEpiLstmBwd) ? *reinterpret_cast<const float4*>(eo.x0 ? eo.x0 + x : zero4)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 dhb = (eo.op == kEpiLstmBwd) ? *reinterpret_cast<const float4*>(eo.x0 ? eo.x0 + x : zero4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            // length-masked variant (encoder BPTT, enc_lstm_bwd_kernel in cells.cu): extra d h / d c from the sequence
+            // outputs at position t, d h_last where the row ends at t; rows that ended earlier produce zero gates
+            bool enc_inactive = false;
+            float4 dcx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (eo.op == kEpiLstmBwd && eo.len) {
+              const long long Lq = eo.len[q];
+              enc_inactive = (Lq <= (long long)eo.t);
+              const long so = (long)q * eo.seq_ld + (long)eo.t * D + n;
+              add4(dhb, *reinterpret_cast<const float4*>(eo.seq_h + so));
+              dcx = *reinterpret_cast<const float4*>(eo.seq_m + so);
+              add4(dhb, *reinterpret_cast<const float4*>((Lq - 1 == (long long)eo.t) ? eo.h_prev + x : zero4));
+            }
             const float4 v = resolve(pr, q, p4);
             if (eo.op == kEpiNone) {
               *reinterpret_cast<float4*>(prm.C + (long)q * prm.ldc + n) = v;
@@ -656,14 +668,18 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
                 d = dh * tc * go * (1.f - go);
                 e = dc * gf;
               };
-              cell(r0.x, r1.x, r2.x, r3.x, r4.x, r5.x, v.x + dhb.x, r6.x, di.x, df.x, dg.x, dgo.x, dcp.x);
-              cell(r0.y, r1.y, r2.y, r3.y, r4.y, r5.y, v.y + dhb.y, r6.y, di.y, df.y, dg.y, dgo.y, dcp.y);
-              cell(r0.z, r1.z, r2.z, r3.z, r4.z, r5.z, v.z + dhb.z, r6.z, di.z, df.z, dg.z, dgo.z, dcp.z);
-              cell(r0.w, r1.w, r2.w, r3.w, r4.w, r5.w, v.w + dhb.w, r6.w, di.w, df.w, dg.w, dgo.w, dcp.w);
+              cell(r0.x, r1.x, r2.x, r3.x, r4.x, r5.x, v.x + dhb.x, r6.x + dcx.x, di.x, df.x, dg.x, dgo.x, dcp.x);
+              cell(r0.y, r1.y, r2.y, r3.y, r4.y, r5.y, v.y + dhb.y, r6.y + dcx.y, di.y, df.y, dg.y, dgo.y, dcp.y);
+              cell(r0.z, r1.z, r2.z, r3.z, r4.z, r5.z, v.z + dhb.z, r6.z + dcx.z, di.z, df.z, dg.z, dgo.z, dcp.z);
+              cell(r0.w, r1.w, r2.w, r3.w, r4.w, r5.w, v.w + dhb.w, r6.w + dcx.w, di.w, df.w, dg.w, dgo.w, dcp.w);
               float* dgt = eo.y1 + (long)q * 4 * D + n;
+              if (enc_inactive) {
+                di = df = dg = dgo = make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {
+                *reinterpret_cast<float4*>(eo.y0 + x) = dcp;
+              }
               *reinterpret_cast<float4*>(dgt) = di; *reinterpret_cast<float4*>(dgt + D) = df;
               *reinterpret_cast<float4*>(dgt + 2 * D) = dg; *reinterpret_cast<float4*>(dgt + 3 * D) = dgo;
-              *reinterpret_cast<float4*>(eo.y0 + x) = dcp;
             } else if (eo.op == kEpiCopy1Bwd) {
               // copy1_bwd_kernel (cells.cu): v = d c_new; r0,r1,r2 = i,f,g; r4 = c2_prev
               float4 di, df, dg, dcp;
