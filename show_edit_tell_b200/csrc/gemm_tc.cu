@@ -11,7 +11,7 @@
 //
 // Both operands are K-major (global rows = tile rows, reduction contiguous): x@W^T (NT) reads the row-major
 // buffers in place; callers present dX / dW work in NT form on transposed copies (MN-major tf32 operands
-// read back as zeros with sm_100a descriptors built this way, tools/debug_tc2.py).
+// read back as zeros with the sm_100a descriptors tried in round 1; that experiment is not kept in the tree).
 //
 // "swap" mode puts the weight matrix on the 128-row P side and the (<=64..128 row) activation batch
 // on the Q side: that is how the skinny per-step GEMMs (M = batch) fill the tensor core's M=128
@@ -1033,7 +1033,7 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   // ... and for plain problems whose C is neither pre-zeroed nor accumulated into: the slab path needs no memset
   // in front of the launch (SET_TC_PLAIN_FUSED=0 restores memset + red.global.add for them).
   static const int plain_fused = getenv("SET_TC_PLAIN_FUSED") ? atoi(getenv("SET_TC_PLAIN_FUSED")) : 1;
-  prm.fused = (fuse_ok && (op != kEpiNone || (plain_fused && !g.beta && !g.c_zeroed))) ? 1 : 0;
+  prm.fused = (fuse_ok && (op != kEpiNone || plain_fused == 2 || (plain_fused && !g.beta && !g.c_zeroed))) ? 1 : 0;
   prm.fuse_ok = fuse_ok ? 1 : 0;
   prm.nblk = gates4 ? 4 : 1;
   prm.blk_stride = gates4 ? g.epi.D : 0;
