@@ -217,6 +217,16 @@ SET_API int set_dcnet_xe_backward(const SetDims* dims, const SetSeqShape* shape,
                           const SetDcNetParams* grads, const int64_t* caps, const int* decode_len_host,
                           const int64_t* prev, const int64_t* prev_len, uint64_t seed,
                           const float* d_predictions, void* workspace, size_t workspace_bytes, void* stream);
+/* One DCNet decode step on explicit state: the DCNet half of the ensemble beam search, eval/eval xe/eval_full.py:141-149
+ * (embed, attention_lstm, caption_attention, language_lstm, fc called one by one on k rows there).  Same contract as
+ * set_editnet_step_begin / set_editnet_step: begin runs the bi-LSTM encoder and the hoisted projections for B rows,
+ * step advances the first `rows` rows in place and writes fc(h2) [rows,V].  shape->T == 2, shape->train == 0. */
+SET_API int set_dcnet_step_begin(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w,
+                         const int64_t* prev, const int64_t* prev_len, void* workspace, size_t workspace_bytes,
+                         void* stream);
+SET_API int set_dcnet_step(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w, const int64_t* tokens,
+                   int rows, float* h1, float* c1, float* h2, float* c2, float* scores, void* workspace,
+                   size_t workspace_bytes, void* stream);
 /* Rollout / its backward: replace DAE.forward of dcnet_rl.py:286-346 (modes as set_editnet_rollout). */
 SET_API int set_dcnet_rollout(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w,
                       const int64_t* prev, const int64_t* prev_len, int64_t start_token, int64_t end_token,

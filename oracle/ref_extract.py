@@ -80,6 +80,42 @@ def dcnet_rl_classes():
     return extract_classes("dcnet_rl.py", DCNET_CLASSES)
 
 
+def eval_full_search(device="cpu"):
+    """The reference's ensemble search, `evaluate_full` of eval/eval xe/eval_full.py:88-215, as a callable
+    `(loader, dae_ar, decoder, beam_size, epoch, word_map) -> results` (list of {"image_id", "caption"}).
+
+    Two edits, both outside the arithmetic under test: the statement `prev_word_inds = top_k_words / vocab_size`
+    (:162) becomes `//` (true division crashes on torch >= 1.5, SURVEY Appendix D), and the function is cut after its
+    per-image loop (the tail needs the COCO tool-chain: Java tokenizer, METEOR)."""
+    path = os.path.join(REFERENCE_ROOT, "eval", "eval xe", "eval_full.py")
+    with open(path, "r") as f:
+        tree = ast.parse(f.read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "evaluate_full"][0]
+    loop_at = max(i for i, n in enumerate(fn.body) if isinstance(n, ast.For))
+    fn.body = fn.body[:loop_at + 1] + [ast.Return(value=ast.Name(id="results", ctx=ast.Load()))]
+
+    class FloorDiv(ast.NodeTransformer):
+        def visit_Assign(self, node):
+            self.generic_visit(node)
+            t = node.targets[0]
+            if isinstance(t, ast.Name) and t.id == "prev_word_inds" and isinstance(node.value, ast.BinOp) \
+                    and isinstance(node.value.op, ast.Div):
+                node.value.op = ast.FloorDiv()
+            return node
+
+    fn = ast.fix_missing_locations(FloorDiv().visit(fn))
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "device": torch.device(device), "tqdm": lambda it, **kw: it}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["evaluate_full"]
+
+
+def eval_class_modules():
+    """the class-only copies the eval scripts import (`from dae import *; from editnet import *`, eval_full.py:18-19)"""
+    e = extract_classes(os.path.join("eval", "eval xe", "editnet.py"), EDITNET_CLASSES)
+    d = extract_classes(os.path.join("eval", "eval xe", "dae.py"), DCNET_CLASSES)
+    return e, d
+
+
 class DropoutScript:
     """Feeds pre-drawn keep-masks to every dropout call of an exec'd reference
     module, in call order, so that a train-mode reference run is reproducible and

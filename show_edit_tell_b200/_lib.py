@@ -160,6 +160,10 @@ _SIGS = {
     "set_dcnet_xe_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams),
                                         C.POINTER(SetDcNetParams), _P, C.POINTER(C.c_int), _P, _P, C.c_uint64, _P, _P,
                                         C.c_size_t, _P]),
+    "set_dcnet_step_begin": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams), _P, _P, _P,
+                                       C.c_size_t, _P]),
+    "set_dcnet_step": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams), _P, C.c_int, _P,
+                                 _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "set_dcnet_rollout": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams), _P, _P,
                                     C.c_int64, C.c_int64, C.c_int, _P, C.c_uint64, _P, _P, _P, C.c_size_t, _P]),
     "set_dcnet_rollout_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams),

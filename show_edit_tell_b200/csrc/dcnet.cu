@@ -464,6 +464,45 @@ int set_dcnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const S
   return dbackward(c, *grads, caps, shape->Wc, 1, prev, prev_len, bt.data(), dl, c.ws.dec_len);
 }
 
+int set_dcnet_step_begin(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w, const int64_t* prev,
+                         const int64_t* prev_len, void* workspace, size_t workspace_bytes, void* stream) {
+  DCtx c;
+  SET_PROPAGATE(make_dctx(c, dims, shape, w, workspace, workspace_bytes, 0, stream));
+  SET_REQUIRE(shape->T == 2 && shape->train == 0, "step sessions use T == 2, eval mode");
+  SET_REQUIRE(prev && prev_len, "null input");
+  return dprepare(c, prev, prev_len);
+}
+
+int set_dcnet_step(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w, const int64_t* tokens,
+                   int rows, float* h1, float* c1, float* h2, float* c2, float* scores, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  DCtx c;
+  SET_PROPAGATE(make_dctx(c, dims, shape, w, workspace, workspace_bytes, 0, stream));
+  SET_REQUIRE(shape->T == 2 && shape->train == 0, "step sessions use T == 2, eval mode");
+  SET_REQUIRE(tokens && h1 && c1 && h2 && c2 && scores && rows >= 1 && rows <= shape->B, "bad args");
+  const size_t B = shape->B, D = dims->D, V = dims->V, LX2 = c.LX2;
+  DWs& s = c.ws;
+  cudaStream_t st = c.st;
+  const size_t row = sizeof(float) * D;
+  // the step runs as t = 1: the "previous" state lives where step 0 would have left it
+  SET_CHECK_CUDA(cudaMemcpy2DAsync(s.X2, sizeof(float) * LX2, h1, row, row, rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.c1 + B * D, c1, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.h2 + B * D, h2, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(s.c2 + B * D, c2, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_PROPAGATE(embed_fwd(tokens, 1, 0, w->embed, dims->V, s.emb_all + B * D, 1, rows, D, 0, 0, kSiteEmb, 0, 0, 1, st));
+  SET_PROPAGATE(dproject_words(c, 1, 1));
+  SET_PROPAGATE(dstep_forward(c, 1, rows));
+  GemmProblem p = gemm_problem(rows, V, scores, V);          // fc(h2), eval: dropout is identity (eval_full.py:149)
+  gemm_add_seg(p, s.h2drop + B * D, D, w->fc_w, D, D);
+  p.bias = w->fc_b;
+  SET_PROPAGATE(gemm(kNT, p, st));
+  SET_CHECK_CUDA(cudaMemcpy2DAsync(h1, row, s.X2 + B * LX2, sizeof(float) * LX2, row, rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(c1, s.c1 + 2 * B * D, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(h2, s.h2 + 2 * B * D, row * rows, cudaMemcpyDeviceToDevice, st));
+  SET_CHECK_CUDA(cudaMemcpyAsync(c2, s.c2 + 2 * B * D, row * rows, cudaMemcpyDeviceToDevice, st));
+  return SET_OK;
+}
+
 int set_dcnet_rollout(const SetDims* dims, const SetSeqShape* shape, const SetDcNetParams* w, const int64_t* prev,
                       const int64_t* prev_len, int64_t start_token, int64_t end_token, int mode,
                       const int64_t* forced, uint64_t seed, int64_t* seq, float* seq_logprobs, void* workspace,

@@ -216,6 +216,46 @@ class DAEBase(nn.Module):
         return call.ws[off.value:off.value + nbytes.value].view(dtype)
 
 
+class DStepSession:
+    """Decode steps of the DCNet on explicit state for `k` rows (the DCNet half of the ensemble beam search,
+    eval/eval xe/eval_full.py:141-149).  Built by `DAEBase.step_session`."""
+
+    def __init__(self, mod, encoded_previous_captions, previous_cap_length):
+        mod._require_cuda(encoded_previous_captions)
+        mod.flatten_parameters()
+        self.mod = mod
+        prev = encoded_previous_captions.contiguous()
+        prev_len = previous_cap_length.contiguous().view(-1)
+        k = prev.shape[0]
+        self.dims = mod._dims()
+        self.shape = SetSeqShape(k, 0, 0, prev.shape[1], int(prev_len.max().item()), 2, 0, 0)
+        nbytes = _lib.lib().set_dcnet_workspace_bytes(C.byref(self.dims), C.byref(self.shape))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=prev.device)
+        check(_lib.lib().set_dcnet_step_begin(C.byref(self.dims), C.byref(self.shape), C.byref(mod._struct), ptr(prev),
+                                              ptr(prev_len), ptr(self.ws), self.ws.numel(), _stream()))
+
+    def init_state(self):
+        k, D = self.shape.B, self.mod.decoder_dim
+        return tuple(torch.zeros(k, D, device=self.ws.device) for _ in range(4))
+
+    def step(self, tokens, state):
+        """tokens (rows,) int64; state = (h1, c1, h2, c2) each (rows, D) -> (scores (rows, V), new state)"""
+        rows = tokens.shape[0]
+        st = [x[:rows].contiguous().clone() for x in state]
+        scores = torch.empty(rows, self.mod.vocab_size, device=self.ws.device)
+        check(_lib.lib().set_dcnet_step(C.byref(self.dims), C.byref(self.shape), C.byref(self.mod._struct),
+                                        ptr(tokens.contiguous()), rows, ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]),
+                                        ptr(scores), ptr(self.ws), self.ws.numel(), _stream()))
+        return scores, tuple(st)
+
+
+def _dstep_session(self, encoded_previous_captions, previous_cap_length):
+    return DStepSession(self, encoded_previous_captions, previous_cap_length)
+
+
+DAEBase.step_session = _dstep_session
+
+
 class DAE(DAEBase):
     """Drop-in for `DAE` of dcnet.py:273-350 (cross-entropy stage)."""
 

@@ -47,3 +47,38 @@ def test_dcnet_xe_live():
         ref = dae.eval()(b["caps"], b["caplens"], b["prev"], b["prev_len"])
         mine = DO.xe_forward(sd, b["caps"], b["caplens"], b["prev"], b["prev_len"])
     assert (ref[0] - mine[0]).abs().max() < 1e-5 and ref[2] == mine[2]
+
+
+def _ensemble_case(seed):
+    V, D, A, Fd, R, Wp = 67, 48, 24, 96, 9, 8
+    sd_e = EO.init_state_dict(V, D, D, D, A, Fd, seed=seed)
+    sd_d = DO.init_state_dict(V, D, D // 2, D, A, seed=seed + 1)
+    b = synth.make_batch(1, V, R, Fd, 11, Wp, ragged=True, seed=seed + 2, min_len=3, min_prev=2)
+    return V, D, A, Fd, sd_e, sd_d, b
+
+
+def test_ensemble_beam_live():
+    """oracle/ensemble_oracle.py against the reference's own evaluate_full loop (eval/eval xe/eval_full.py)"""
+    from oracle import ensemble_oracle as XO
+    search = RX.eval_full_search()
+    ens, dns = RX.eval_class_modules()
+    for seed in (41, 47, 53):
+        V, D, A, Fd, sd_e, sd_d, b = _ensemble_case(seed)
+        wm = synth.word_map(V)
+        dec = ens["DecoderC"](wm, D, D, D, A, Fd)
+        dec.load_state_dict(sd_e, strict=False)
+        dae = dns["DAE"](wm, None, decoder_dim=D, attention_dim=A, caption_features_dim=D // 2, emb_dim=D)
+        dae.load_state_dict(sd_d, strict=False)
+
+        class AR(torch.nn.Module):          # DAEWithAR's constructor loads a checkpoint; only `.dae` is used (:108)
+            def __init__(self, dae):
+                super().__init__()
+                self.dae = dae
+
+        loader = [(b["feats"], torch.tensor([[7]]), b["prev"], b["prev_len"])]
+        with torch.no_grad():
+            res = search(loader, AR(dae), dec, 3, 0, wm)
+            seq, score = XO.beam_search_ensemble(sd_e, sd_d, wm, b["feats"], b["prev"], b["prev_len"], beam_size=3)
+        rev = {v: k for k, v in wm.items()}
+        mine = " ".join(rev[w] for w in seq if w not in (wm["<start>"], wm["<end>"], wm["<pad>"]))
+        assert res[0]["caption"] == mine and res[0]["image_id"] == 7, (res, mine)
