@@ -248,46 +248,28 @@ def main():
     def step_resident():
         trainer.step(*resident)
 
-    # End to end: every step's inputs start in pinned host memory and its loss ends on the host.  The loop is
-    # pipelined the way a training loop with a prefetching loader is: while step i computes, the inputs of step
-    # i+1 cross PCIe on a copy stream into the other half of a double buffer, and the loss of step i-1 (copied
-    # to pinned memory behind its step) is read.  All copies of the timed steps are inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [[torch.empty(host[k].shape, dtype=host[k].dtype, device=dev) for k in keys] for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    # End to end through the public API: every step's inputs start in pinned host memory (feed.DevicePrefetcher copies
+    # batch i+1 host->device on a copy stream while step i computes) and its loss ends on the host (copied to pinned
+    # memory behind its step, read one step later).  All copies of the timed steps are inside the timed region.
+    from show_edit_tell_b200.feed import DevicePrefetcher
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
-    e2e = {"i": 0, "last": None}
 
-    def prefetch(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])      # the step that used this half has finished with it
-            for dst, k in zip(bufs[slot], keys):
-                dst.copy_(host[k], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def step_e2e():
-        i = e2e["i"]
-        slot = i % 2
-        if i == 0:
-            prefetch(0)
-        stream.wait_event(ready[slot])
-        prefetch(1 - slot)
-        loss = trainer.step(*bufs[slot])
-        consumed[slot].record(stream)
-        loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
-        loss_ev[slot].record(stream)
-        if i > 0:                                       # device->host read of the previous step's result
-            loss_ev[1 - slot].synchronize()
-            e2e["last"] = float(loss_host[1 - slot])
-        e2e["i"] = i + 1
-
-    def drain_e2e():
-        if e2e["i"] > 0:
-            slot = (e2e["i"] - 1) % 2
-            loss_ev[slot].synchronize()
-            e2e["last"] = float(loss_host[slot])
+    def run_e2e(n_steps):
+        last = None
+        feed_iter = DevicePrefetcher((tuple(host[k] for k in keys) for _ in range(n_steps)), dev)
+        for i, batch in enumerate(feed_iter):
+            slot = i % 2
+            loss = trainer.step(*batch)
+            loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ev[slot].record(stream)
+            if i > 0:                                       # device->host read of the previous step's result
+                loss_ev[1 - slot].synchronize()
+                last = float(loss_host[1 - slot])
+        if n_steps > 0:                                     # the last loss is on the host before the clock stops
+            loss_ev[(n_steps - 1) % 2].synchronize()
+            last = float(loss_host[(n_steps - 1) % 2])
+        return last
 
     for _ in range(args.warmup):
         step_resident()
@@ -302,18 +284,11 @@ def main():
     fwd_ms, bwd_ms = C.c_float(), C.c_float()
     L.set_profile_read(C.byref(fwd_ms), C.byref(bwd_ms))
     L.set_profile_enable(0)
-    for _ in range(2):
-        step_e2e()
-
-    def e2e_steps():
-        step_e2e()
-
+    run_e2e(2)
     barrier()
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_e0.record(stream)
-    for _ in range(args.steps):
-        e2e_steps()
-    drain_e2e()                      # the last loss is on the host before the clock stops
+    run_e2e(args.steps)
     t_e1.record(stream)
     barrier()
     ms_t = torch.tensor([t_e0.elapsed_time(t_e1)], device=dev)
@@ -341,8 +316,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "captions/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "pipeline": "double-buffered H2D on a copy stream overlapped with the previous step; loss read "
-                            "back one step behind"},
+                "pipeline": "feed.DevicePrefetcher: H2D of batch i+1 on a copy stream while step i computes; loss "
+                            "read back one step behind"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "decode step, forward (launch chain of one timestep: 5 tcgen05 GEMM launches with "
                                                "the LSTM / copy-LSTM cells fused in their cluster epilogues + attention + "
