@@ -3,11 +3,11 @@
 //
 //   D[p, q] = sum_k P[p, k] * Q[q, k]           P tile = UMMA "A" (128 rows), Q tile = UMMA "B" (QN rows)
 //
-// Every fp32 operand x is split on chip into hi = tf32(x) (low 13 mantissa bits cleared, written
-// back in place over the TMA'd tile) and lo = x - hi (exact in fp32; written to a sibling tile), and
-// each K-step issues  D += P_lo*Q_hi ;  D += P_hi*Q_lo ;  D += P_hi*Q_hi  -- the dropped lo*lo term is
-// 2^-22 relative, so results match fp32 FMA accumulation to ~1e-6 (one-pass
-// TF32 misses the 1e-4 parity budget by 10x, 3xTF32 meets it).
+// Every fp32 operand x is used as hi = tf32(x) -- the raw word: kind::tf32 ignores the low 13 mantissa bits -- and
+// lo = x - (x with those bits cleared) (exact in fp32), and each K-step issues
+// D += P_lo*Q_hi ;  D += P_hi*Q_lo ;  D += P_hi*Q_hi  -- the dropped lo*lo term is 2^-22 relative, so results match
+// fp32 FMA accumulation to ~1e-6 (one-pass TF32 misses the 1e-4 parity budget by 10x, 3xTF32
+// meets it).
 //
 // Both operands are K-major (global rows = tile rows, reduction contiguous): x@W^T (NT) reads the row-major
 // buffers in place; callers present dX / dW work in NT form on transposed copies (MN-major tf32 operands
@@ -21,9 +21,13 @@
 // fp32 tile once, split it in registers and write hi | lo into TENSOR memory (tcgen05.st), from where the
 // MMA takes its A operand; only the small Q tile is split in place in shared memory.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = hi/lo converters
-// (groups of 4 warps alternate K-blocks) during the main loop, then the epilogue (TMEM -> registers ->
-// shared -> global).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (both walk the K-blocks warp-uniformly and
+// issue from one elect.sync lane), warps 2.. = hi/lo converters (groups of 4 warps alternate K-blocks) during the main
+// loop, then the epilogue: TMEM -> registers -> shared, then one of three finishes -- plain stores / red.global.add
+// (split-K into pre-zeroed or accumulating C), the scratch-slab cooperative finish, or the thread-block-cluster finish
+// through distributed shared memory -- the last two optionally applying a fused LSTM-family cell (GemmEpi).
+// Launches carry the programmatic-dependent-launch attribute: constant weight tiles are requested before
+// griddepcontrol.wait (common.cuh).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
