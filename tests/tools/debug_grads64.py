@@ -1,8 +1,8 @@
 """Is a gradient mismatch a bug or fp32 noise?  Compare the CUDA path and the fp32 oracle against
 an fp64 run of the oracle (full dims, eval mode)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import torch
 from oracle import editnet_oracle as EO, synth
 from show_edit_tell_b200 import editnet

@@ -3,8 +3,7 @@ process and report run-to-run deviations: split-K atomics give ~1e-6 noise, anyt
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import dcnet_oracle as DO, editnet_oracle as EO, synth
-from show_edit_tell_b200 import dcnet, editnet
+from show_edit_tell_b200 import dcnet, editnet, synth
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 which = sys.argv[2] if len(sys.argv) > 2 else "both"
@@ -91,16 +90,12 @@ def run(name, mod, args):
     print("%s: %d runs, %d glitches (> 1e-4), worst deviation %.3e" % (name, N, bad, worst))
 
 if which in ("both", "dcnet"):
-    sd = DO.init_state_dict(V, D, 512, 1024, A, seed=9)
-    mod = dcnet.DAE(wm, None, D, A, 512, 1024)
-    mod.load_state_dict(sd, strict=False)
-    mod = mod.cuda()
+    torch.manual_seed(9)
+    mod = dcnet.DAE(wm, None, D, A, 512, 1024).cuda()
     b = synth.make_batch(4, V, 1, 4, 20, 18, ragged=False, seed=72)
     run("dcnet eval B=4", mod, [b[k].cuda() for k in ("caps", "caplens", "prev", "prev_len")])
 if which in ("both", "editnet"):
-    sd = EO.init_state_dict(V, D, D, D, A, Fd, seed=5)
-    mod = editnet.DecoderC(wm, D, D, D, A, Fd)
-    mod.load_state_dict(sd, strict=False)
-    mod = mod.cuda()
+    torch.manual_seed(5)
+    mod = editnet.DecoderC(wm, D, D, D, A, Fd).cuda()
     b = synth.make_batch(8, V, 36, Fd, 20, 18, ragged=True, seed=21)
     run("editnet eval B=8", mod, [b[k].cuda() for k in ("feats", "caps", "caplens", "prev", "prev_len")] + [False, 0.0])
