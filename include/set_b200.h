@@ -242,6 +242,18 @@ SET_API int set_dcnet_rollout_backward(const SetDims* dims, const SetSeqShape* s
 SET_API int set_reward_criterion(int B, int T, const float* seq_logprobs, const int64_t* seq, const float* reward,
                          float* loss_out, float* d_logprobs, void* stream);
 
+/* Self-critical CIDEr-D reward from token ids: replaces get_self_critical_reward() of editnet_rl.py:611-646 together with
+ * preprocess_gd (:587-600), array_to_str (:602-609) and the CiderD.compute_score call (pyciderevalcap, `df='coco-train-idxs'`).
+ * gen / greedy [B][L] int64 rollouts (0 = <end>/pad as the rollout writes them); all_caps [B][R][Wc] int64 reference captions
+ * as the data loader delivers them (<start> .. <end> <pad>..); df_keys / df_vals: open-addressing table (capacity a power of
+ * two, empty key = ~0, linear probing behind splitmix64(key)) mapping a packed n-gram -- sum_j (token_j + 1) << (16 j) --
+ * to its document frequency; ref_len = number of documents.  Writes scores [2B] (CIDEr-D x 10 of the B sampled then the B
+ * greedy captions) and rewards [B][L] = weight * (score_sample - score_greedy) broadcast over the steps. */
+SET_API int set_ciderd_reward(int B, int L, int R, int Wc, const int64_t* gen, const int64_t* greedy,
+                      const int64_t* all_caps, int64_t start_tok, int64_t end_tok, int64_t pad_tok,
+                      const uint64_t* df_keys, const float* df_vals, uint64_t df_capacity, double ref_len, double sigma,
+                      float cider_weight, float* scores, float* rewards, void* stream);
+
 /* Global-norm clip + Adam over one flat parameter buffer: replaces clip_grad_norm_(0.25) +
  * Adam.step(), editnet.py:580-581.  Gradients are first multiplied by grad_scale and, when
  * count_dev != NULL, divided by *count_dev (a device float: the all-reduced token count of a

@@ -168,6 +168,8 @@ _SIGS = {
                                     C.c_int64, C.c_int64, C.c_int, _P, C.c_uint64, _P, _P, _P, C.c_size_t, _P]),
     "set_dcnet_rollout_backward": (C.c_int, [C.POINTER(SetDims), C.POINTER(SetSeqShape), C.POINTER(SetDcNetParams),
                                              C.POINTER(SetDcNetParams), _P, _P, C.c_uint64, _P, _P, C.c_size_t, _P]),
+    "set_ciderd_reward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P,
+                                    C.c_uint64, C.c_double, C.c_double, C.c_float, _P, _P, _P]),
     "set_reward_criterion": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "set_clip_adam": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _P, _P, _P]),
