@@ -257,8 +257,12 @@ SET_API int set_ciderd_reward(int B, int L, int R, int Wc, const int64_t* gen, c
 /* Global-norm clip + Adam over one flat parameter buffer: replaces clip_grad_norm_(0.25) +
  * Adam.step(), editnet.py:580-581.  Gradients are first multiplied by grad_scale and, when
  * count_dev != NULL, divided by *count_dev (a device float: the all-reduced token count of a
- * data-parallel step whose ranks contributed loss SUMS).  `scratch` holds >= 4
- * floats; scratch[1] receives the pre-clip total norm. */
+ * data-parallel step whose ranks contributed loss SUMS; a zero count leaves the
+ * parameters unchanged).  `scratch` holds >= SET_CLIP_ADAM_SCRATCH_FLOATS floats: scratch[1]
+ * receives the pre-clip total norm, scratch[8..] the per-block partial sums of squares, which
+ * every block then adds in one fixed order -- the clip coefficient is a deterministic function
+ * of the gradient bits, so data-parallel replicas stay bit-identical. */
+#define SET_CLIP_ADAM_SCRATCH_FLOATS 2048
 SET_API int set_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
                   int step, float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale,
                   const float* count_dev, float* scratch, void* stream);
@@ -290,6 +294,9 @@ SET_API int set_gemm_trace(void* buf);
    [2100 + 8k + s] SM-clock stamps of K-block k of CTA 0 */
 SET_API int set_gemm_trace_seq(void* buf, long stride_u64, int launches);
 SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
+/* tensor-core launches that took the two-CTAs-per-SM ("twin") configuration since the last reset (parity tests
+   assert that the big time-batched GEMMs of the benchmarked configuration really ran on it) */
+SET_API long long set_gemm_twin_launches(int reset);
 /* C = A @ B^T style contraction through the library's GEMM engine (mode 0 NT, 1 NN, 2 TN). */
 SET_API int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,
              const float* bias, float* C, long ldc, int beta, int act, void* stream);

@@ -178,6 +178,7 @@ _SIGS = {
     "set_gemm_trace": (C.c_int, [_P]),
     "set_gemm_trace_seq": (C.c_int, [_P, C.c_long, C.c_int]),
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
+    "set_gemm_twin_launches": (C.c_longlong, [C.c_int]),
     "set_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_long, _P, C.c_long, _P, _P, C.c_long,
                            C.c_int, C.c_int, _P]),
 }

@@ -1052,15 +1052,10 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
   const int n = a.P > a.R ? a.P : a.R;
   const size_t smem = sizeof(float) * (2 * a.A + 2 * ((n + 3) & ~3) + 40 + 2 * kAttnThreads);
   SET_REQUIRE(smem <= 48 * 1024, "attention smem");
-  // d alpha scratch between the two kernels (library-owned, grown on demand; single-stream use like the GEMM scratch)
-  static float* dal = nullptr;
-  static size_t dal_cap = 0;
+  // d alpha scratch between the two kernels (library-owned per (device, stream), grown on demand)
   const size_t need = (size_t)a.b * (a.P + a.R);
-  if (need > dal_cap) {
-    if (dal) SET_CHECK_CUDA(cudaFree(dal));
-    dal_cap = need < 65536 ? 65536 : 2 * need;
-    SET_CHECK_CUDA(cudaMalloc(&dal, sizeof(float) * dal_cap));
-  }
+  float* dal = static_cast<float*>(lib_scratch(kScratchAttnDal, s, sizeof(float) * (need < 65536 ? 65536 : 2 * need), false));
+  if (!dal) return SET_ERR_CUDA;
   const int cs = a.att1c ? kCapSlices : 0, vs = a.att1v ? kVisSlices : 0;
   if (cs + vs == 0) return SET_OK;
   SET_CHECK_CUDA(launch_chain(attention_bwd_dal_kernel, dim3(a.b, cs + vs), dim3(kAttnThreads), 0, s, a, dal, cs));

@@ -2,8 +2,8 @@
 // GPU round trip of get_self_critical_reward(), editnet_rl.py:611-646 (+ preprocess_gd :587-600, array_to_str :602-609)
 // and the CiderD.compute_score() it calls (pyciderevalcap, un-vendored; algorithm restated in oracle/ciderd_oracle.py).
 //
-// Integer / hash work, tiny: one CTA per hypothesis (B sampled + B greedy), 128 threads = one per n-gram occurrence
-// (a sentence of <= 32 tokens has <= 122 occurrences of n-grams with n = 1..4).  An n-gram of token ids is packed
+// Integer / hash work, tiny: one CTA per hypothesis (B sampled + B greedy), 256 threads = one per n-gram occurrence
+// (a sentence of <= 64 tokens has <= 250 occurrences of n-grams with n = 1..4).  An n-gram of token ids is packed
 // exactly into 64 bits (16 bits per token, +1 so that token 0 -- the <end> the reference keeps as a word -- is
 // distinct from "absent"); document frequencies come from an open-addressing table built on the host from the
 // reference's `coco-train-idxs` pickle format.  All arithmetic in fp64, like the numpy reference.
@@ -13,9 +13,9 @@
 namespace set {
 namespace {
 
-constexpr int kCdMaxLen = 32;
+constexpr int kCdMaxLen = 64;   // tokens per sentence: the loader's caption width is 52 (max_len 50 + <start>/<end>)
 constexpr int kCdMaxNg = 4 * kCdMaxLen;
-constexpr int kCdThreads = 128;
+constexpr int kCdThreads = 256;  // >= n-gram occurrences of a 64-token sentence (64 + 63 + 62 + 61 = 250)
 constexpr unsigned long long kCdEmpty = ~0ull;
 
 struct CdSent {
@@ -161,7 +161,8 @@ extern "C" int set_ciderd_reward(int B, int L, int R, int Wc, const int64_t* gen
   SET_REQUIRE(B > 0 && L > 0 && R > 0 && Wc > 0 && gen && greedy && all_caps && df_keys && df_vals && scores && rewards, "bad args");
   SET_REQUIRE(df_capacity > 0 && (df_capacity & (df_capacity - 1)) == 0, "table capacity must be a power of two");
   SET_REQUIRE(ref_len > 0 && sigma > 0, "ref_len / sigma");
-  SET_REQUIRE(L <= set::kCdMaxLen, "rollouts longer than 32 tokens are not supported by the n-gram kernel");
+  SET_REQUIRE(L <= set::kCdMaxLen, "rollouts longer than 64 tokens are not supported by the n-gram kernel");
+  SET_REQUIRE(Wc <= set::kCdMaxLen, "reference captions wider than 64 tokens would be truncated by the n-gram kernel");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   set::ciderd_score_kernel<<<2 * B, set::kCdThreads, 0, st>>>(
       B, L, R, Wc, gen, greedy, all_caps, start_tok, end_tok, pad_tok, reinterpret_cast<const unsigned long long*>(df_keys),

@@ -46,6 +46,15 @@ extern "C" void set_count_launch(int n);  // bumps the library-wide kernel-launc
 
 namespace set {
 
+// Library-owned device scratch (split-K slabs + arrival counters of the tensor-core GEMM, the d-alpha buffer between
+// the two attention-backward kernels, ...).  One allocation per (device, stream, tag): two streams or two devices of one
+// process never share a buffer, so the C ABI may be driven from several streams / threads / devices at once.  Grows on
+// demand (cudaFree of the old block synchronises the device); `zero` clears a fresh block.  nullptr on failure
+// (set_last_error() says why).
+enum ScratchTag : int { kScratchTcSlabs = 1, kScratchTcCounters = 2, kScratchAttnDal = 3, kScratchStepBarrier = 4,
+                        kScratchStepSlabs = 5, kScratchStepMaps = 6 };
+void* lib_scratch(int tag, cudaStream_t stream, size_t bytes, bool zero);
+
 // ---------------------------------------------------------------------------------
 // Programmatic dependent launch.  The decode step is a chain of short dependent kernels; each
 // kernel of the chain is launched with the programmatic-serialization attribute, signals its

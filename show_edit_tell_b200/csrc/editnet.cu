@@ -1128,6 +1128,12 @@ int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset) 
   return SET_OK;
 }
 
+long long set_gemm_twin_launches(int reset) {
+  const long long v = g_tc_twin_launches;
+  if (reset) g_tc_twin_launches = 0;
+  return v;
+}
+
 int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,
              const float* bias, float* C, long ldc, int beta, int act, void* stream) {
   GemmProblem p = gemm_problem(M, N, C, ldc);

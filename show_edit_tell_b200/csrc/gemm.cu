@@ -249,7 +249,7 @@ int colsum_batch(const ColJob* jobs, int n, cudaStream_t stream) {
 
 int g_backend = 0;              // 0: tensor cores where eligible, 1: CUDA cores only
 int g_pdl = getenv("SET_PDL") ? atoi(getenv("SET_PDL")) : 1;
-long long g_tc_launches = 0, g_simt_launches = 0;
+long long g_tc_launches = 0, g_simt_launches = 0, g_tc_twin_launches = 0;
 
 int gemm_group(int mode, const GemmProblem* probs_in, int n, cudaStream_t stream) {
   SET_REQUIRE(n >= 1 && n <= 8, "1..8 problems per group");

@@ -92,7 +92,7 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
 void gemm_tc_set_trace(unsigned long long* buf);
 void gemm_tc_set_trace_seq(unsigned long long* buf, long stride, int launches);
 extern int g_backend;
-extern long long g_tc_launches, g_simt_launches;
+extern long long g_tc_launches, g_simt_launches, g_tc_twin_launches;
 
 // Launch up to 8 independent problems of one mode (tensor cores where eligible, else one grouped
 // CUDA-core grid).

@@ -36,6 +36,7 @@
 #include <type_traits>
 
 #include "gemm.cuh"
+#include "tc_common.cuh"
 
 namespace set {
 
@@ -88,11 +89,6 @@ struct TcParams {
   unsigned long long* trace;       // debugging aid: per-phase %globaltimer stamps of CTA 0 (SET_TC_TRACE)
 };
 
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 #define TC_STAMP(slot)                                                         \
   do {                                                                         \
     if (prm.trace && blockIdx.x == 0) prm.trace[slot] = gtimer();              \
@@ -104,115 +100,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
   do {                                                                                          \
     if (prm.trace && blockIdx.x == 0 && (i) < 48) prm.trace[2100 + 8 * (i) + (slot)] = clock64(); \
   } while (0)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// K-major / MN-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
-  return d;
-}
-// A operand from tensor memory: [128 lanes] x [8 columns of tf32] at `tmem_a`
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-// tensor-memory columns [0,QN): accumulator; [QN + 64*slot, +64): P_hi | P_lo of a Q/TMEM slot
-
-// one lane of a converged warp; ptxas then treats the guarded block as warp-uniform (tcgen05.mma issues
-// straight from uniform registers, no per-lane replay loop around it)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-  return r;
-}
-// predicated distributed-shared-memory loads (zero when !on)
-__device__ __forceinline__ float2 dsmem_ld2(uint32_t addr, bool on) {
-  float2 v;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
-      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
-      "@p ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n\t}"
-      : "=f"(v.x), "=f"(v.y) : "r"(addr), "r"((int)on) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr, bool on) {
-  float4 v;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
-      "@p ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "r"((int)on) : "memory");
-  return v;
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
-      "%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // TWIN = 1: a shallower pipeline sized so that TWO CTAs share an SM (half the shared memory, 256 tensor-memory
 // columns each).  Used for the big time-batched GEMMs (many tiles per SM): one CTA's prologue / epilogue / MMA
@@ -920,24 +807,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-bool g_tc_ready = false, g_tc_failed = false;
 // split-K scratch of the fused epilogue: one [128][128] fp32 slab and one arrival counter per CTA of a launch.
-// Launches are stream-ordered (a launch's epilogue begins after its grid dependency resolved), so one slab set
-// serves every launch of the calling stream; the library is used from one stream at a time.
+// Launches of one stream are ordered (a launch's epilogue begins after its grid dependency resolved), so one slab set
+// serves every launch of a (device, stream) pair; the set is keyed by that pair (lib_scratch), so several streams,
+// threads or devices of one process never share slabs or counters.
 constexpr int kScratchSlots = 320;
-int g_sm_count = 0;
-int g_max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [c]: clusters of c CTAs (one CTA per SM) resident at once
-float* g_tc_scratch = nullptr;
-int* g_tc_counters = nullptr;
-std::once_flag g_tc_once;
+constexpr int kMaxDevices = 64;
+struct TcDevice {
+  std::once_flag once;
+  bool ready = false;
+  int sm_count = 0;
+  int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // [c]: clusters of c CTAs (one CTA per SM) resident at once
+};
+TcDevice g_tc_dev[kMaxDevices];
 
-void tc_init() {
+// per-device set-up: function attributes live in the device's context, cluster occupancy depends on its SM layout
+void tc_init(TcDevice* d, int dev) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-    g_tc_failed = true;
-    return;
-  }
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   bool ok = true;
   auto set_attr = [&](auto kern, int bytes) {
@@ -949,15 +837,7 @@ void tc_init() {
   set_attr(gemm_tc_kernel<64, 8>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8>, TcCfg<128>::kSmemBytes);
   set_attr(gemm_tc_kernel<128, 1, 1>, TcCfg<128, 1>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 2, 1>, TcCfg<128, 1>::kSmemBytes);
   set_attr(gemm_tc_kernel<128, 5, 1>, TcCfg<128, 1>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8, 1>, TcCfg<128, 1>::kSmemBytes);
-  ok = ok && cudaMalloc(&g_tc_scratch, sizeof(float) * (size_t)kScratchSlots * kTileP * 128) == cudaSuccess;
-  // (+ 16 bytes of zeros behind the counters: TcParams::zero16)
-  ok = ok && cudaMalloc(&g_tc_counters, sizeof(int) * (2 * kScratchSlots + 4)) == cudaSuccess;
-  ok = ok && cudaMemset(g_tc_counters, 0, sizeof(int) * (2 * kScratchSlots + 4)) == cudaSuccess;
-  {
-    int dev = 0;
-    ok = ok && cudaGetDevice(&dev) == cudaSuccess &&
-         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
-  }
+  ok = ok && cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
   for (int c = 2; ok && c <= 8; c <<= 1) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -968,17 +848,22 @@ void tc_init() {
     cfg.attrs = at; cfg.numAttrs = 1;
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, gemm_tc_kernel<64, 1>, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
-    g_max_clusters[c] = nc;
+    d->max_clusters[c] = nc;
   }
   if (getenv("SET_TC_VERBOSE"))
-    fprintf(stderr, "libset_b200: %d SMs, resident clusters of 2/4/8 CTAs: %d/%d/%d\n", g_sm_count, g_max_clusters[2],
-            g_max_clusters[4], g_max_clusters[8]);
-  if (!ok) {
-    cudaGetLastError();
-    g_tc_failed = true;
-    return;
-  }
-  g_tc_ready = true;
+    fprintf(stderr, "libset_b200: device %d: %d SMs, resident clusters of 2/4/8 CTAs: %d/%d/%d\n", dev, d->sm_count,
+            d->max_clusters[2], d->max_clusters[4], d->max_clusters[8]);
+  if (!ok) { cudaGetLastError(); return; }
+  d->ready = true;
+}
+
+// the current device's state (nullptr: tensor-core path unavailable -> callers use the CUDA-core kernel)
+TcDevice* tc_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return nullptr; }
+  TcDevice* d = &g_tc_dev[dev];
+  std::call_once(d->once, tc_init, d, dev);
+  return d->ready ? d : nullptr;
 }
 
 // rows x cols fp32 matrix with row stride ld (elements); box = box_cols x box_rows
@@ -1042,8 +927,7 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
   prm.nblk = gates4 ? 4 : 1;
   prm.blk_stride = gates4 ? g.epi.D : 0;
   prm.epi = g.epi; prm.epi.op = op;
-  prm.scratch = g_tc_scratch; prm.counters = g_tc_counters;
-  prm.zero16 = reinterpret_cast<const float*>(g_tc_counters + 2 * kScratchSlots);
+  // (scratch / counters / zero16 are filled per (device, stream) by gemm_tc_try_group)
   for (int s = 0; s < g.nseg; ++s) {
     const GemmSeg& sg = g.seg[s];
     prm.K[s] = sg.K;
@@ -1071,8 +955,10 @@ static bool tc_plan(int mode, const GemmProblem& g, int QN, TcParams& prm) {
 // h1, say) thereby stream their weights concurrently instead of paying a launch each.
 int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cudaStream_t stream) {
   for (int i = 0; i < n; ++i) taken[i] = false;
-  std::call_once(g_tc_once, tc_init);
-  if (!g_tc_ready) return SET_OK;
+  TcDevice* tcd = tc_device();
+  if (!tcd) return SET_OK;
+  const int g_sm_count = tcd->sm_count;
+  const int* g_max_clusters = tcd->max_clusters;
   // one Q-tile width per launch: 64 if every problem's small side fits, else 128
   int QN = 64;
   for (int i = 0; i < n; ++i) {
@@ -1081,7 +967,7 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     const int small = g.M < g.N ? g.M : g.N;
     if (small > 64) QN = 128;
   }
-  static TcGroup<8> grp;  // host staging (launch copies it); calls are serialised by the caller's stream use
+  static thread_local TcGroup<8> grp;  // host staging (the launch copies it)
   grp.n = 0;
   long tiles_total = 0;
   int idx[8];
@@ -1157,9 +1043,15 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
       }
     }
   }
+  // library-owned scratch of this (device, stream): slabs, two counters per CTA (+ 16 bytes of zeros: TcParams::zero16)
+  float* tc_scratch = static_cast<float*>(lib_scratch(kScratchTcSlabs, stream, sizeof(float) * (size_t)kScratchSlots * kTileP * 128, false));
+  int* tc_counters = static_cast<int*>(lib_scratch(kScratchTcCounters, stream, sizeof(int) * (2 * kScratchSlots + 4), true));
+  if (!tc_scratch || !tc_counters) return SET_ERR_CUDA;
   int cta = 0;
   for (int k = 0; k < grp.n; ++k) {
     TcParams& prm = grp.p[k];
+    prm.scratch = tc_scratch; prm.counters = tc_counters;
+    prm.zero16 = reinterpret_cast<const float*>(tc_counters + 2 * kScratchSlots);
     const GemmProblem& g = probs[idx[k]];
     const int split = splits[k];
     prm.split_k = split;
@@ -1211,7 +1103,7 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     static const int twin_on = getenv("SET_TC_TWIN") ? atoi(getenv("SET_TC_TWIN")) : 1;
     bool any_fused = false;
     for (int k = 0; k < grp.n; ++k) any_fused = any_fused || grp.p[k].fused;
-    if (twin_on && !any_fused && cta > g_sm_count)
+    if (twin_on && !any_fused && cta > g_sm_count && (++g_tc_twin_launches, true))
       return launch_chain(gemm_tc_kernel<128, G, 1>, dim3(cta), dim3(kThreadsTc), TcCfg<128, 1>::kSmemBytes, stream, small);
     return launch_chain(gemm_tc_kernel<128, G>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, small);
   };

@@ -1,8 +1,10 @@
 // Error reporting, version, and the fused optimizer tail of the train step:
 // global-norm clip + Adam over one flat buffer (train() tail, editnet.py:580-581).
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 
 #include "../../include/set_b200.h"
 #include "common.cuh"
@@ -35,9 +37,32 @@ extern "C" long long set_launch_count(int reset) {
 }
 
 namespace set {
+
+void* lib_scratch(int tag, cudaStream_t stream, size_t bytes, bool zero) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void*, size_t>> blocks;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_record_error("lib_scratch: cudaGetDevice failed"); return nullptr; }
+  std::lock_guard<std::mutex> lk(mu);
+  auto& e = blocks[std::make_tuple(dev, stream, tag)];
+  if (e.second >= bytes && e.first) return e.first;
+  if (e.first) cudaFree(e.first);   // synchronises the device: no in-flight kernel still reads the old block
+  e.first = nullptr; e.second = 0;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); set_record_error("lib_scratch: cudaMalloc failed"); return nullptr; }
+  if (zero && cudaMemset(p, 0, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(p); set_record_error("lib_scratch: cudaMemset failed"); return nullptr; }
+  e.first = p; e.second = bytes;
+  return p;
+}
+
 namespace {
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+// Global-norm clip, stage 1: block b writes the sum of squares of its (fixed) grid-stride share to part[b].  Stage 2
+// lives in adam_kernel: every block adds the partials in the same fixed order, so the clip coefficient is a pure
+// function of the gradient bits -- data-parallel replicas that hold bit-identical all-reduced gradients stay
+// bit-identical (a float atomicAdd across blocks would make the coefficient depend on arrival order).
+constexpr int kOptBlocks = 148 * 8;
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ part) {
   __shared__ float red[40];
   float s = 0.f;
   const size_t n4 = n >> 2;
@@ -50,7 +75,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
        x += (size_t)gridDim.x * blockDim.x)
     s += g[x] * g[x];
   s = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
 // torch.optim.Adam (defaults, no amsgrad / weight decay) after clip_grad_norm_:
@@ -62,8 +87,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float max_norm, float grad_scale,
                                                    const float* __restrict__ count_dev,
                                                    float* __restrict__ scratch) {
-  if (count_dev) grad_scale /= count_dev[0];
-  const float total = sqrtf(scratch[0]) * fabsf(grad_scale);
+  __shared__ float red[40];
+  float part = 0.f;
+  for (int b = threadIdx.x; b < kOptBlocks; b += blockDim.x) part += scratch[8 + b];   // same order in every block
+  const float sumsq = block_sum(part, red);
+  // DP: ranks contributed sums; a zero global count (every shard empty) leaves the parameters untouched
+  if (count_dev) grad_scale = count_dev[0] > 0.f ? grad_scale / count_dev[0] : 0.f;
+  const float total = sqrtf(sumsq) * fabsf(grad_scale);
   const float coef = fminf(max_norm / (total + 1e-6f), 1.0f) * grad_scale;
   if (blockIdx.x == 0 && threadIdx.x == 0) scratch[1] = total;
   const float step = lr / bc1;
@@ -101,9 +131,8 @@ extern "C" int set_clip_adam(float* params, const float* grads, float* exp_avg, 
   SET_REQUIRE(params && grads && exp_avg && exp_avg_sq && scratch && step >= 1, "bad args");
   SET_REQUIRE((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "grads must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  SET_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(float), st));
-  const int blocks = 148 * 8;
-  set::sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, scratch);
+  const int blocks = set::kOptBlocks;
+  set::sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, scratch + 8);
   SET_CHECK_CUDA(cudaGetLastError());
   set_count_launch(1);
   const float bc1 = 1.f - powf(beta1, (float)step);

@@ -487,6 +487,7 @@ def beam_search(decoder, word_map, image_features, encoded_previous_caption, pre
     complete_seqs, complete_scores = [], []
     state = sess.init_state()
     step = 1
+    runaway = False
     while True:
         scores, state = sess.step(k_prev_words, state)                                      # :645-653
         scores = torch.log_softmax(scores, dim=1)                                           # :654
@@ -514,9 +515,12 @@ def beam_search(decoder, word_map, image_features, encoded_previous_caption, pre
         top_k_scores = top_k_scores[inc].unsqueeze(1)
         k_prev_words = next_word_inds[inc]
         if step > max_steps:                                                                # :702
+            runaway = True
             break
         step += 1
-    if not complete_scores:
-        return seqs[0].tolist(), float(top_k_scores[0])
+    if runaway or not complete_scores:
+        # the 50-step guard: the reference emits the first 18 tokens of the best live beam even when other beams
+        # completed earlier (:702-713)
+        return seqs[0][:18].tolist(), float(top_k_scores[0])
     i = complete_scores.index(max(complete_scores))                                         # :706
     return complete_seqs[i], complete_scores[i]

@@ -84,10 +84,14 @@ class AdaptiveTrainSet(torch.utils.data.Dataset):
 
 def collate_adaptive(data, root=".", max_regions=100, feat_dim=2048, pin=None):
     """`collate_fn_train`, editnet_adaptive.py:58-80: -> (images (B,100,2048), images_mean (B,2048), captions, caplens,
-    previous_captions, prev_caplens, all_captions); float32, pinned when a CUDA device is present."""
+    previous_captions, prev_caplens, all_captions); float32, pinned when a CUDA device is present and the call runs in the
+    main process."""
     image_id, caption, caplen, previous_caption, prev_caplen, all_captions = zip(*data)
     B = len(caption)
-    pin = torch.cuda.is_available() if pin is None else pin
+    if pin is None:
+        # pin only in the main process: a forked DataLoader worker must not touch CUDA ("Cannot re-initialize CUDA in
+        # forked subprocess"); with num_workers > 0 use DataLoader(pin_memory=True) as the reference does
+        pin = torch.cuda.is_available() and torch.utils.data.get_worker_info() is None
     images = torch.zeros(B, max_regions, feat_dim, pin_memory=pin)
     images_mean = torch.zeros(B, feat_dim, pin_memory=pin)
     for i, img_id in enumerate(image_id):

@@ -14,6 +14,7 @@ kernel divides by it on the device.  The result equals the single-process step o
 concatenated batch.
 """
 import ctypes as C
+import warnings
 
 import torch
 import torch.distributed as dist
@@ -37,15 +38,40 @@ class XETrainer:
 
     def _ensure_state(self):
         flat = self.decoder.flatten_parameters()
-        if self._state is None or self._state["flat_ptr"] != flat.data_ptr():
+        old = self._state
+        if old is None or old["flat_ptr"] != flat.data_ptr():
             n = flat.numel()
             dev = flat.device
             # +64: slot n holds the token count that rides along with the gradients
             self._state = dict(flat_ptr=flat.data_ptr(), n=n,
                                grad=torch.zeros(n + 64, device=dev), m=torch.zeros(n, device=dev),
-                               v=torch.zeros(n, device=dev), scratch=torch.zeros(8, device=dev),
+                               v=torch.zeros(n, device=dev), scratch=torch.zeros(2048, device=dev),
                                loss=torch.zeros(2, device=dev))
+            if old is not None and old["n"] == n:
+                # the flat parameter buffer was re-created (decoder.to(...), re-flatten): the Adam moments describe the
+                # same parameters, so they move with it and step_count stays valid
+                self._state["m"].copy_(old["m"])
+                self._state["v"].copy_(old["v"])
+            elif old is not None:
+                warnings.warn("parameter layout changed: Adam state reset")
+                self.step_count = 0
         return flat, self._state
+
+    # optimizer checkpointing (the reference pickles the optimizer object, editnet.py:168-175)
+    def state_dict(self):
+        _, st = self._ensure_state()
+        return {"step": self.step_count, "exp_avg": st["m"].clone(), "exp_avg_sq": st["v"].clone(),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "max_norm": self.max_norm}
+
+    def load_state_dict(self, sd):
+        _, st = self._ensure_state()
+        if sd["exp_avg"].numel() != st["n"]:
+            raise ValueError("optimizer state has %d elements, the model has %d" % (sd["exp_avg"].numel(), st["n"]))
+        st["m"].copy_(sd["exp_avg"])
+        st["v"].copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step"])
+        self.lr, self.betas, self.eps = sd.get("lr", self.lr), tuple(sd.get("betas", self.betas)), sd.get("eps", self.eps)
+        self.max_norm = sd.get("max_norm", self.max_norm)
 
     def step(self, image_features, encoded_captions, caption_lengths, encoded_previous_captions,
              previous_cap_length, image_mean=None, seed=None):
@@ -53,6 +79,8 @@ class XETrainer:
         dec = self.decoder
         dec.train()
         flat, st = self._ensure_state()
+        if image_features.shape[0] == 0:
+            return self._empty_shard_step(flat, st)
         call = dec._prepare_xe(image_features, image_mean, encoded_captions, caption_lengths,
                                encoded_previous_captions, previous_cap_length, seed=seed)
         L = _lib.lib()
@@ -81,10 +109,24 @@ class XETrainer:
                                        ptr(count_dev), ptr(st["scratch"]), _stream()))
         self.last_call = call
         dec._last_call = call
-        loss = st["loss"][0]
+        loss = st["loss"][0].clone()      # a fresh tensor: losses collected across steps must not alias one buffer
         if self.distributed:
             loss = loss / st["loss"][1]
         return loss
+
+    def _empty_shard_step(self, flat, st):
+        """a rank whose shard has no rows (shard_rows with more ranks than rows): nothing to compute, but the rank
+        still contributes zeros and a zero count to the collective and applies the same update as its peers"""
+        if not self.distributed:
+            raise ValueError("empty batch")
+        st["grad"].zero_()
+        st["loss"].zero_()
+        count_dev = allreduce_sums(st["grad"], st["n"], st["loss"][1], self.group)
+        self.step_count += 1
+        check(_lib.lib().set_clip_adam(ptr(flat), ptr(st["grad"]), ptr(st["m"]), ptr(st["v"]), st["n"], self.step_count,
+                                       self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
+                                       ptr(count_dev), ptr(st["scratch"]), _stream()))
+        return st["loss"][0].clone()
 
     def grad_norm(self):
         return self._state["scratch"][1]
@@ -145,7 +187,9 @@ class SCSTTrainer:
                               ptr(st["scratch"]), _stream()))
         self.last_call, self.last_seq, self.last_greedy = call, seq, greedy_seq
         dec._last_call = call
-        return st["loss"][0]
+        return st["loss"][0].clone()
 
+    state_dict = XETrainer.state_dict
+    load_state_dict = XETrainer.load_state_dict
     grad_norm = XETrainer.grad_norm
     flat_grad = XETrainer.flat_grad

@@ -312,7 +312,7 @@ def test_clip_adam_kernel_matches_oracle():
     m = torch.zeros(n)
     v = torch.zeros(n)
     P, M, Vv = p.cuda(), m.cuda(), v.cuda()
-    scratch = torch.zeros(8, device="cuda")
+    scratch = torch.zeros(2048, device="cuda")
     for step in (1, 2, 3):
         g = torch.randn(n, generator=g0) * (0.001 if step == 2 else 0.05)
         G = torch.zeros(n + 64, device="cuda")
@@ -323,6 +323,39 @@ def test_clip_adam_kernel_matches_oracle():
         assert abs(float(scratch[1]) - float(total)) < 1e-5 * float(total)
         assert (P.cpu() - p).abs().max() < 1e-6
         assert (M.cpu() - m).abs().max() < 1e-7
+
+
+def test_clip_adam_count_dev_branch_and_determinism():
+    """data-parallel form: gradients of the loss SUM divided by a device-side count (optim.cu `count_dev`), a zero count
+    (every shard empty) leaves the parameters alone, and the clip coefficient is bit-reproducible run to run"""
+    _lib, *_ = _imports()
+    g0 = torch.Generator().manual_seed(19)
+    n = 300007
+    p0 = torch.randn(n, generator=g0)
+    g = torch.randn(n, generator=g0) * 0.05
+    count = 37.0
+    results = []
+    for rep in range(3):
+        P, M, Vv = p0.clone().cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+        G = torch.zeros(n + 64, device="cuda")
+        G[:n] = (g * count).cuda()
+        G[n] = count
+        scratch = torch.zeros(2048, device="cuda")
+        _lib.check(_lib.lib().set_clip_adam(_lib.ptr(P), _lib.ptr(G), _lib.ptr(M), _lib.ptr(Vv), n, 1, 5e-4, 0.9, 0.999,
+                                            1e-8, 0.25, 1.0, _lib.ptr(G[n:n + 1]), _lib.ptr(scratch), None))
+        results.append((P.cpu(), float(scratch[1])))
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    total = EO.clip_and_adam([p], [g.clone()], [m], [v], step=1)
+    assert abs(results[0][1] - float(total)) < 1e-5 * float(total)
+    assert (results[0][0] - p).abs().max() < 1e-6
+    for P, tn in results[1:]:
+        assert tn == results[0][1] and torch.equal(P, results[0][0]), "clip + Adam is not bit-reproducible"
+    P = p0.clone().cuda()
+    G = torch.zeros(n + 64, device="cuda")
+    scratch = torch.zeros(2048, device="cuda")
+    M, Vv = torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    _lib.check(_lib.lib().set_clip_adam(_lib.ptr(P), _lib.ptr(G), _lib.ptr(M), _lib.ptr(Vv), n, 1, 5e-4, 0.9, 0.999, 1e-8, 0.25, 1.0, _lib.ptr(G[n:n + 1]), _lib.ptr(scratch), None))
+    assert torch.equal(P.cpu(), p0) and torch.isfinite(P).all()
 
 
 def test_trainer_step_matches_oracle_step(small_sd, small_cfg):

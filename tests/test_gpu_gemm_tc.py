@@ -24,7 +24,7 @@ def _stats(L, reset=True):
 
 SHAPES = [  # (mode, M, N, K)
     (0, 64, 4096, 2048), (0, 64, 4096, 3072), (0, 64, 512, 1024), (0, 37, 1024, 1024), (0, 8, 256, 96),
-    (0, 1216, 1000, 1024), (0, 300, 260, 200), (0, 128, 128, 64), (0, 129, 65, 100),
+    (0, 1216, 1000, 1024), (0, 2304, 1024, 2048), (0, 300, 260, 200), (0, 128, 128, 64), (0, 129, 65, 100),
     (1, 64, 4096, 4096), (1, 64, 1024, 512), (1, 1216, 1024, 1000), (1, 40, 2048, 4096),
     (2, 4096, 1024, 1216), (2, 512, 1024, 4608), (2, 1000, 1024, 1216), (2, 96, 160, 70),
 ]
@@ -67,6 +67,39 @@ def test_tc_gemm_matches_fp64(mode, M, N, K):
     L.check(lib.set_gemm(mode, M, N, K, L.ptr(A), lda, L.ptr(Bm), ldb, None, L.ptr(C1), N, 0, 1, None))
     ref1 = (ref - bias.double() - C0.double()).clamp_min(0)
     assert float((C1.double() - ref1).abs().max()) < tol
+
+
+# the big time-batched GEMMs of the benchmarked train step (B=64, T=19, V=10000): more tiles than SMs -> two CTAs per SM
+TWIN_SHAPES = [(43776, 512, 1024), (1216, 10000, 1024), (2432, 1024, 2048), (1216, 4096, 1216), (2500, 1000, 300)]
+
+
+@pytest.mark.parametrize("M,N,K", TWIN_SHAPES)
+def test_tc_gemm_twin_configuration_matches_fp64(M, N, K):
+    L = _L()
+    lib = L.lib()
+    lib.set_gemm_backend(0)
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.double() @ W.double().t() + bias.double()
+    tol = 2e-5 * float(ref.abs().max()) * max(1.0, K / 2048)
+    for rep in range(3):     # repeated: the twin CTAs of an SM interleave differently from launch to launch
+        Cm = torch.full((M, N), float("nan"), device="cuda")
+        _stats(L)
+        lib.set_gemm_twin_launches(1)
+        L.check(lib.set_gemm(0, M, N, K, L.ptr(A), K, L.ptr(W), K, L.ptr(bias), L.ptr(Cm), N, 0, 0, None))
+        torch.cuda.synchronize()
+        tc, simt = _stats(L)
+        assert (tc, simt) == (1, 0)
+        assert int(lib.set_gemm_twin_launches(1)) == 1, "not launched in the twin configuration"
+        err = float((Cm.double() - ref).abs().max())
+        assert err < tol, ("twin", M, N, K, rep, err, tol)
+    # accumulate (beta = 1) + relu-free epilogue on a second buffer
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    C1 = C0.clone()
+    L.check(lib.set_gemm(0, M, N, K, L.ptr(A), K, L.ptr(W), K, None, L.ptr(C1), N, 1, 0, None))
+    assert float((C1.double() - (ref - bias.double() + C0.double())).abs().max()) < tol
 
 
 def test_unaligned_problem_falls_back_to_cuda_cores():
