@@ -294,6 +294,14 @@ SET_API int set_gemm_trace(void* buf);
    [2100 + 8k + s] SM-clock stamps of K-block k of CTA 0 */
 SET_API int set_gemm_trace_seq(void* buf, long stride_u64, int launches);
 SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
+/* persistent decode-step kernel (csrc/step_kernel.cu): launches since the last reset and the timesteps they covered
+   (0 launches: the shape fell outside the persistent path and the per-step launch chain ran) */
+SET_API int set_step_stats(long long* launches, long long* steps, int reset);
+/* CTAs and CTAs-per-cluster of the persistent launch on the current device (0, 0: not available) */
+SET_API int set_step_geometry(int* grid, int* cluster);
+/* debugging: device buffer of >= steps * 8 * grid uint64; every CTA stamps %globaltimer at each phase boundary of each
+   timestep: [(step * 8 + phase) * grid + cta], phases 0..6 = end of A, B, C1, C2, D, E, F.  NULL switches it off. */
+SET_API int set_step_trace(void* buf);
 /* tensor-core launches that took the two-CTAs-per-SM ("twin") configuration since the last reset (parity tests
    assert that the big time-batched GEMMs of the benchmarked configuration really ran on it) */
 SET_API long long set_gemm_twin_launches(int reset);

@@ -11,6 +11,7 @@
 // [h1 | att_cap | att_img] is written in place by the producing kernels, and GEMM
 // K-segments read [h2 ; h1] or column blocks of weight_ih where they lie.
 #include "seq_common.cuh"
+#include "step_kernel.cuh"
 
 namespace set {
 
@@ -21,7 +22,7 @@ struct Ws {
   float *emb_prev, *enc_xg, *enc_gates, *enc_h, *enc_c, *prev_h, *prev_m, *mask, *fh, *att1c;
   float *image_mean, *fe_pre, *att1, *fe_t, *pre1s, *emb_all, *pre1, *gw, *tw;
   float *gates1, *c1, *X2, *s2, *g2, *alpha_c, *ctx_c, *sel, *alpha_v, *zst, *cnew, *kgate, *c2, *h2, *h2drop;
-  float *logits, *lse, *scratch4d, *s4, *ones;
+  float *logits, *lse, *scratch4d, *s4, *ones, *att_sc;
   int *sel_idx, *nreg, *dec_len, *unfinished, *unf_count;
   int64_t *it, *tok_raw;
   // ---- zeroed at the start of backward (region B)
@@ -88,6 +89,7 @@ void layout(const SetDims& d, const SetSeqShape& s, Arena& ar, Ws& w) {
   w.scratch4d = ar.take<float>("scratch4d", B * 4 * D);
   w.s4 = ar.take<float>("s4", T * B * 3 * D);
   w.ones = ar.take<float>("ones", T * B);
+  w.att_sc = ar.take<float>("att_sc", B * (P + R));
   w.sel_idx = ar.take<int>("sel_idx", T * B);
   w.nreg = ar.take<int>("nreg", B);
   w.dec_len = ar.take<int>("dec_len", B);
@@ -427,6 +429,160 @@ int step_forward(Ctx& c, const float* feats, int t, int b) {
                               s.h2 + (size_t)(t + 1) * B * D, s.h2drop + (size_t)t * B * D, b, D, c.s.train, c.seed,
                               (long)t * B * D, st));
   }
+  return SET_OK;
+}
+
+// ------------------------------------------------------------------ persistent decode-step kernel (step_kernel.cu)
+// Steps [t0, t0 + nt) in ONE cooperative launch.  *launched = 0 (and SET_OK) when the shape is outside what the
+// persistent kernel covers: the caller then runs the launch chain (step_forward).
+int steps_persistent(Ctx& c, const float* feats, int t0, int nt, const int* bt, int* launched) {
+  *launched = 0;
+  static const int on = getenv("SET_STEP_PERSIST") ? atoi(getenv("SET_STEP_PERSIST")) : 1;
+  const int B = c.s.B, P = c.s.P, R = c.s.R, T = c.s.T, D = c.d.D, A = c.d.A, F = c.d.F;
+  const int LS2 = c.LS2, LX2 = c.LX2;
+  if (!on || g_backend != 0 || nt < 1) return SET_OK;
+  if (B > 64 || D % 256 != 0 || A % 128 != 0 || F % 256 != 0 || P > 128 || R > 128 || P < 1 || R < 1) return SET_OK;
+  int grid = 0, cluster = 0;
+  if (!step_kernel_available(&grid, &cluster)) return SET_OK;
+  {
+    // per-CTA table sizes of the attention phase (step_kernel.cu: kAttnMaxItems / kAttnMaxUnits)
+    const int items = (B * (F / 256 + D / 256) + grid - 1) / grid + 2;
+    const int nchv = (R + 35) / 36, nchc = (P + 35) / 36;
+    if (items > 32 || items * (nchv > nchc ? nchv : nchc) > 96) return SET_OK;
+  }
+  const SetEditNetParams& w = *c.w;
+  Ws& s = c.ws;
+  static thread_local StepParams prm;
+  memset(&prm, 0, sizeof(prm));
+  bool ok = true;
+  auto map2 = [&](int idx, const float* ptr, int rows, int cols, int box_rows) {
+    const unsigned long long dims[2] = {(unsigned long long)cols, (unsigned long long)rows};
+    const unsigned long long st[1] = {(unsigned long long)cols * 4ull};
+    const unsigned int box[2] = {32u, (unsigned)box_rows};
+    ok = ok && tc_encode_map(&prm.maps[idx], ptr, 2, dims, st, box, true);
+  };
+  auto map3 = [&](int idx, const float* ptr, int cols, int rows, int outer, long ld_row, long ld_outer, int box_cols, int box_rows,
+                  bool swz) {
+    const unsigned long long dims[3] = {(unsigned long long)cols, (unsigned long long)rows, (unsigned long long)outer};
+    const unsigned long long st[2] = {(unsigned long long)ld_row * 4ull, (unsigned long long)ld_outer * 4ull};
+    const unsigned int box[3] = {(unsigned)box_cols, (unsigned)box_rows, 1u};
+    ok = ok && tc_encode_map(&prm.maps[idx], ptr, 3, dims, st, box, swz);
+  };
+  enum { mWih = 0, mWhh, mCaDec, mVaDec, mGate128, mTc, mX2h128, mH2h, mGate64, mSc64, mGcm, mX2h32, mGcn,
+         mQh2, mQX2, mQctx, mQsel, mQcnew, mFeats, mPrevH };
+  map2(mWih, w.al_wih, 4 * D, 3 * D + F, 32);   map2(mWhh, w.al_whh, 4 * D, D, 32);
+  map2(mCaDec, w.ca_dec_w, A, D, 128);          map2(mVaDec, w.va_dec_w, A, D, 128);
+  map2(mGate128, w.ca_gate_w, D, 3 * D, 128);   map2(mTc, w.ca_tc_w, D, 2 * D, 128);
+  map2(mX2h128, w.cl_x2h_w, 4 * D, LX2, 128);   map2(mH2h, w.cl_h2h_w, 4 * D, D, 128);
+  map2(mGate64, w.ca_gate_w, D, 3 * D, 64);     map2(mSc64, w.ca_sc_w, D, D, 64);
+  map2(mGcm, w.cl_gcm_w, D, D, 128);            map2(mX2h32, w.cl_x2h_w, 4 * D, LX2, 32);
+  map2(mGcn, w.cl_gcn_w, D, D, 128);
+  map3(mQh2, s.h2, D, B, T + 1, D, (long)B * D, 32, 64, true);
+  map3(mQX2, s.X2, LX2, B, T, LX2, (long)B * LX2, 32, 64, true);
+  map3(mQctx, s.ctx_c, D, B, T, D, (long)B * D, 32, 64, true);
+  map3(mQsel, s.sel, D, B, T, D, (long)B * D, 32, 64, true);
+  map3(mQcnew, s.cnew, D, B, T, D, (long)B * D, 32, 64, true);
+  const int chunk_v = R < 36 ? R : 36, chunk_c = P < 36 ? P : 36;
+  map3(mFeats, feats, F, R, B, F, (long)R * F, 256, chunk_v, false);
+  map3(mPrevH, s.prev_h, D, P, B, D, (long)P * D, 256, chunk_c, false);
+  if (!ok) return SET_OK;   // (tensor-core path unavailable: the chain decides what to do)
+  auto TP = [](float* p, long st) { TPtr x; x.p = p; x.st = st; return x; };
+  auto seg = [&](StepProb& p, int K, int pm0, int pc0, int qm, int qc0, int qtoff, int pm1 = 0, int pc1 = 0) {
+    const int sg = p.nseg++;
+    p.nkb[sg] = (K + 31) / 32;
+    p.pmap[sg][0] = pm0; p.pcol0[sg][0] = pc0; p.pmap[sg][1] = pm1; p.pcol0[sg][1] = pc1;
+    p.qmap[sg] = qm; p.qcol0[sg] = qc0; p.qtoff[sg] = qtoff;
+  };
+  const long BD = (long)B * D;
+  int np = 0;
+  {  // phase A: attention-LSTM recurrent part (editnet.py:532) + cell
+    StepProb& p = prm.prob[np];
+    seg(p, D, mWih, 2 * D, mQh2, 0, 0);
+    seg(p, D, mWhh, 0, mQX2, 0, -1);
+    p.nblk = 4; p.blk_stride = D; p.N = D; p.epi = kSEpiLstm;
+    p.C = TP(s.gates1, 4 * BD); p.ldc = 4 * D;
+    p.add = TP(s.pre1, 4 * BD); p.ldadd = 4 * D;
+    p.a0 = TP(s.c1, BD); p.a1 = TP(s.c1 + BD, BD); p.a2 = TP(s.X2, (long)B * LX2); p.ld0 = LX2;
+    prm.phase[0].nprob = 1; prm.phase[0].prob[0] = np++;
+  }
+  {  // phase B: everything that consumes h1
+    StepPhase& ph = prm.phase[1];
+    const long s2st = (long)B * LS2;
+    StepProb* p = &prm.prob[np];
+    seg(*p, D, mCaDec, 0, mQX2, 0, 0); p->nblk = 1; p->N = A; p->bias = w.ca_dec_b; p->C = TP(s.s2, s2st); p->ldc = LS2;
+    ph.prob[ph.nprob++] = np++;
+    p = &prm.prob[np];
+    seg(*p, D, mVaDec, 0, mQX2, 0, 0); p->nblk = 1; p->N = A; p->bias = w.va_dec_b; p->C = TP(s.s2 + A, s2st); p->ldc = LS2;
+    ph.prob[ph.nprob++] = np++;
+    p = &prm.prob[np];
+    seg(*p, D, mGate128, D, mQX2, 0, 0); p->nblk = 1; p->N = D; p->C = TP(s.s2 + 2 * A, s2st); p->ldc = LS2;
+    p->add = TP(s.gw, BD); p->ldadd = D;
+    ph.prob[ph.nprob++] = np++;
+    p = &prm.prob[np];
+    seg(*p, D, mTc, D, mQX2, 0, 0); p->nblk = 1; p->N = D; p->C = TP(s.s2 + 2 * A + D, s2st); p->ldc = LS2;
+    p->add = TP(s.tw, BD); p->ldadd = D;
+    ph.prob[ph.nprob++] = np++;
+    p = &prm.prob[np];
+    seg(*p, D, mX2h128, 0, mQX2, 0, 0);
+    seg(*p, D, mH2h, 0, mQh2, 0, 0);
+    p->nblk = 1; p->N = 4 * D; p->bias = w.cl_x2h_b; p->bias2 = w.cl_h2h_b; p->C = TP(s.g2, 4 * BD); p->ldc = 4 * D;
+    ph.prob[ph.nprob++] = np++;
+  }
+  {  // phase D: context gate (two-block tiles), gate_cmem(sel), x2h[:, 2D:] att_img
+    StepPhase& ph = prm.phase[2];
+    StepProb* p = &prm.prob[np];
+    seg(*p, D, mGate64, 2 * D, mQctx, 0, 0, mSc64, 0);
+    p->nblk = 2; p->N = D; p->epi = kSEpiCtxGate;
+    p->add = TP(s.s2 + 2 * A, (long)B * LS2); p->ldadd = LS2; p->bias2 = w.ca_sc_b;
+    p->a0 = TP(s.s2 + 2 * A + D, (long)B * LS2); p->ld0 = LS2;
+    p->a1 = TP(s.zst, 3 * BD); p->a2 = TP(s.X2 + D, (long)B * LX2); p->ld1 = LX2;
+    ph.prob[ph.nprob++] = np++;
+    p = &prm.prob[np];
+    seg(*p, D, mGcm, 0, mQsel, 0, 0); p->nblk = 1; p->N = D; p->bias = w.cl_gcm_b; p->bias2 = w.cl_gcn_b;
+    p->C = TP(s.s4 + 2 * D, 3 * BD); p->ldc = 3 * D;
+    ph.prob[ph.nprob++] = np++;
+    p = &prm.prob[np];
+    seg(*p, F, mX2h128, 2 * D, mQX2, 2 * D, 0); p->nblk = 1; p->N = 4 * D; p->C = TP(s.g2, 4 * BD); p->ldc = 4 * D; p->beta = 1;
+    ph.prob[ph.nprob++] = np++;
+  }
+  {  // phase E: x2h[:, D:2D] att_cap + copy-LSTM stage 1
+    StepProb& p = prm.prob[np];
+    seg(p, D, mX2h32, D, mQX2, D, 0);
+    p.nblk = 4; p.blk_stride = D; p.N = D; p.epi = kSEpiCopy1; p.beta = 1;
+    p.C = TP(s.g2, 4 * BD); p.ldc = 4 * D;
+    p.a0 = TP(s.c2, BD); p.a1 = TP(s.cnew, BD);
+    prm.phase[3].nprob = 1; prm.phase[3].prob[0] = np++;
+  }
+  {  // phase F: gate_cnew(c_new) + copy gate, c2, h2, dropout(h2)
+    StepProb& p = prm.prob[np];
+    seg(p, D, mGcn, 0, mQcnew, 0, 0);
+    p.nblk = 1; p.N = D; p.epi = kSEpiCopy2; p.beta = 1;
+    p.C = TP(s.s4 + 2 * D, 3 * BD); p.ldc = 3 * D;
+    p.a0 = TP(s.g2, 4 * BD); p.ld0 = 4 * D;
+    p.a1 = TP(s.sel, BD); p.a2 = TP(s.cnew, BD); p.a3 = TP(s.kgate, BD);
+    p.a4 = TP(s.c2 + BD, BD); p.a5 = TP(s.h2 + BD, BD); p.a6 = TP(s.h2drop, BD);
+    prm.phase[4].nprob = 1; prm.phase[4].prob[0] = np++;
+  }
+  StepAttn& a = prm.attn;
+  a.P = P; a.R = R; a.A = A; a.D = D; a.F = F;
+  a.s2 = TP(s.s2, (long)B * LS2); a.ld_s2 = LS2;
+  a.att1c = s.att1c; a.att1v = TP(s.att1, c.s.train ? (long)B * R * A : 0);
+  a.cap_w = w.ca_full_w; a.cap_b = w.ca_full_b; a.vis_w = w.va_full_w; a.vis_b = w.va_full_b;
+  a.mask = s.mask; a.nreg = c.s.adaptive ? s.nreg : nullptr; a.sc = s.att_sc;
+  a.map_feats = mFeats; a.map_prevh = mPrevH; a.chunk_v = chunk_v; a.chunk_c = chunk_c;
+  a.prev_m = s.prev_m;
+  a.alpha_c = TP(s.alpha_c, (long)B * P); a.ctx = TP(s.ctx_c, BD); a.sel = TP(s.sel, BD);
+  a.alpha_v = TP(s.alpha_v, (long)B * R); a.att_img = TP(s.X2 + 2 * D, (long)B * LX2); a.ld_img = LX2;
+  a.sel_idx = s.sel_idx; a.sel_idx_st = B;
+  prm.B = B; prm.D = D; prm.train = c.s.train; prm.seed = c.seed;
+  if (step_plan_splits(prm, grid, cluster) != SET_OK) return SET_OK;   // (fewer SMs than a phase has tiles: chain)
+  for (int done = 0; done < nt; done += 64) {
+    const int n = nt - done < 64 ? nt - done : 64;
+    prm.t0 = t0 + done; prm.nt = n;
+    for (int k = 0; k < n; ++k) prm.bt[k] = bt[done + k];
+    SET_PROPAGATE(step_launch(prm, grid, cluster, c.st));
+  }
+  *launched = 1;
   return SET_OK;
 }
 
@@ -898,7 +1054,14 @@ static int xe_forward_impl(const SetDims* dims, const SetSeqShape* shape, const 
                             c.st));
     SET_PROPAGATE(project_words(c, 0, T));
     SET_PROPAGATE(profile_mark(0, c.st));
-    for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
+    int persistent = 0;
+    {
+      int nsteps = 0;   // steps that decode at least one row (bt is non-increasing)
+      while (nsteps < T && bt[nsteps] > 0) ++nsteps;
+      SET_PROPAGATE(steps_persistent(c, feats, 0, nsteps, bt.data(), &persistent));
+    }
+    if (!persistent)
+      for (int t = 0; t < T; ++t) SET_PROPAGATE(step_forward(c, feats, t, bt[t]));
     SET_PROPAGATE(profile_mark(1, c.st));
   } else {
     // scheduled sampling (editnet.py:508-520): step t's input may be drawn from step t-1's scores, so
@@ -1125,6 +1288,26 @@ int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset) 
   if (tc_launches) *tc_launches = g_tc_launches;
   if (simt_launches) *simt_launches = g_simt_launches;
   if (reset) g_tc_launches = g_simt_launches = 0;
+  return SET_OK;
+}
+
+int set_step_stats(long long* launches, long long* steps, int reset) {
+  if (launches) *launches = g_step_launches;
+  if (steps) *steps = g_step_steps;
+  if (reset) g_step_launches = g_step_steps = 0;
+  return SET_OK;
+}
+
+int set_step_geometry(int* grid, int* cluster) {
+  int g = 0, c = 0;
+  const bool ok = step_kernel_available(&g, &c);
+  if (grid) *grid = ok ? g : 0;
+  if (cluster) *cluster = ok ? c : 0;
+  return SET_OK;
+}
+
+int set_step_trace(void* buf) {
+  step_set_trace(reinterpret_cast<unsigned long long*>(buf));
   return SET_OK;
 }
 

@@ -37,6 +37,7 @@
 
 #include "gemm.cuh"
 #include "tc_common.cuh"
+#include "step_kernel.cuh"
 
 namespace set {
 
@@ -884,6 +885,17 @@ int g_tc_trace_left = 0;
 bool aligned_ok(const float* p, long ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 4) == 0; }
 
 }  // namespace
+
+bool tc_encode_map(CUtensorMap* m, const float* ptr, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned int* box, bool swizzle128) {
+  if (!tc_device() || rank < 2 || rank > 3) return false;
+  cuuint64_t d[3]; cuuint64_t st[2]; cuuint32_t bx[3]; cuuint32_t es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(ptr), d, st, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // Fills `prm` for one problem; returns false if the problem is not eligible for the tensor-core path
 // (caller falls back to the CUDA-core kernel).  `QN` is the Q-tile width chosen for the whole group.

@@ -134,8 +134,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // generic-proxy global writes <-> async-proxy (TMA) reads of the same memory inside one kernel
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// ---- spin waits with a watchdog: a protocol bug must trap, never hang the GPU (2 s of %globaltimer)
+// ---- spin waits with a watchdog: a protocol bug must trap, never hang the GPU (2 s of %globaltimer).  The check is
+// out of line: the wait loops are instantiated at dozens of sites of a persistent kernel whose code must stay small
+// enough for the instruction cache.
 constexpr unsigned long long kSpinTimeoutNs = 2000000000ull;
+__device__ __noinline__ static void spin_watchdog(unsigned long long* t0) {
+  const unsigned long long now = gtimer();
+  if (*t0 == 0) *t0 = now;
+  else if (now - *t0 > kSpinTimeoutNs) __trap();
+}
 __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity) {
   uint32_t done;
   unsigned long long t0 = 0;
@@ -146,13 +153,48 @@ __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return;
-    if ((it & 1023u) == 1023u) {
-      const unsigned long long now = gtimer();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > kSpinTimeoutNs) __trap();
-    }
+    if ((it & 1023u) == 1023u) spin_watchdog(&t0);
   }
 }
+// cluster-scope mbarrier signalling between the CTAs of a thread-block cluster (distributed shared memory)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t target_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar), "r"(target_rank) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t local_bar, uint32_t target_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar), "r"(target_rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_guarded(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  unsigned long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) spin_watchdog(&t0);
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -161,16 +203,22 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// wait until *p >= target (monotonic counter), one thread
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until *p >= target (monotonic counter), one thread.  Polls with relaxed loads (an acquire load per poll would
+// invalidate the SM's L1 every iteration) and fences once when the value is there.
 __device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target) {
   unsigned long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
-    if ((int32_t)(ld_acquire_gpu(p) - target) >= 0) return;
-    if ((it & 255u) == 255u) {
-      const unsigned long long now = gtimer();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > kSpinTimeoutNs) __trap();
+    if ((int32_t)(ld_relaxed_gpu(p) - target) >= 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      return;
     }
+    __nanosleep(20);
+    if ((it & 255u) == 255u) spin_watchdog(&t0);
   }
 }
 
