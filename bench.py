@@ -1,20 +1,23 @@
 #!/usr/bin/env python
-"""Headline benchmark: captions/s of one complete EditNet cross-entropy train step
-(BASELINE.json `metric`; workload = configs[1]: B=64 per GPU, seq_len 20 -> 19 decode steps,
-36x2048 features, V=10000), plus the roofline of the decode step and the CPU baseline.
+"""Benchmarks of the EditNet / DCNet decode path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+Default workload `xe` is the headline (BASELINE.json `metric`, configs[1]): captions/s of one complete EditNet
+cross-entropy train step, B=64 per GPU, seq_len 20 -> 19 decode steps, 36x2048 features, V=10000.  The other
+BASELINE.json configs run with --workload: `greedy256` (configs[2]), `scst` (configs[3]), `adaptive` (configs[4]),
+`dcnet4` (configs[0]).  One JSON line on stdout (rank 0) with the same schema for every workload: metric / value
+(inputs resident in HBM) / e2e (host buffers, copies inside the timed region) / roofline / cpu_baseline / clocks.
+See DESIGN.md "Measurement" for how every field is obtained.
 """
 import argparse
 import ctypes as C
+import csv
 import json
 import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import torch
@@ -23,19 +26,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 V, D, A, FD, R, B, CAPW, PREVW = 10000, 1024, 512, 2048, 36, 64, 20, 18
-METRIC = "captions/sec (EditNet XE train, B=64, 36x2048 feats)"
+KEYS = ("feats", "caps", "caplens", "prev", "prev_len")
 
-# algorithmic bytes of one teacher-forced decode step, train mode, fp32,
-# time-invariant products hoisted: W_rec (weights that multiply step-dependent activations, read once)
-# + b * S (per-sample activations).  In this build the per-step re-projection of the dropped-out
-# region embedding is itself hoisted into one time-batched GEMM, so the eval-mode W_rec applies and S
-# carries the per-step att1 slice instead of att_embed.
-W_REC_BYTES = 36_700_160 * 4            # 146.80 MB
-S_BYTES = 544_768                       # per sample-step (eval/hoisted figure of §8d)
+# algorithmic bytes of one decode step, fp32, time-invariant products hoisted:
+# W_rec (weights that multiply step-dependent activations, each read once) + b * S (per-sample activations).
+W_REC_TF = 36_700_160 * 4                 # teacher forced: 146.80 MB
+W_REC_AR = 53_231_616 * 4                 # autoregressive (+ token-dependent slices + fc): 212.93 MB
 
 
-def step_bytes(b):
-    return W_REC_BYTES + b * S_BYTES
+def s_bytes(regions=36, autoregressive=False):
+    """per sample-step: region rows + their hoisted projection + encoder rows + their projection + state / hoisted terms"""
+    s = regions * FD * 4 + regions * A * 4 + 18 * D * 4 + 18 * A * 4 + 4096 + 32768 + 16384 + 8192 + 4096
+    return s + (4 * V if autoregressive else 0)
+
+
+WORKLOADS = {
+    "xe": dict(config=1, metric="captions/sec (EditNet XE train, B=64, 36x2048 feats)",
+               text="EditNet XE train step (fwd + packed CE + bwd + clip 0.25 + Adam), B=64/GPU, seq_len=20 (T=19), "
+                    "36x2048 feats, V=10000, dropout on"),
+    "greedy256": dict(config=2, metric="captions/sec (EditNet greedy decode, B=256, max_len 18)",
+                      text="EditNet greedy decode (eval path, editnet_rl.py:485-549 sample_max), B=256, max_len=18 "
+                           "(hard-coded at editnet_rl.py:487), 36x2048 feats, V=10000"),
+    "scst": dict(config=3, metric="captions/sec (EditNet SCST train step, greedy + sampled rollout, B=64/GPU)",
+                 text="EditNet self-critical step (editnet_rl.py:649-679): greedy rollout + sampled rollout (dropout on) "
+                      "+ device CIDEr-D reward + RewardCriterion + bwd + clip 0.25 + Adam, B=64/GPU, max_len=18, "
+                      "36x2048 feats, V=10000, 5 synthetic references per image"),
+    "adaptive": dict(config=4, metric="captions/sec (EditNet adaptive XE train, ragged 10-100 regions, B=64)",
+                     text="EditNet adaptive XE train step (editnet_adaptive.py:489-562), ragged 10..100 region features "
+                          "zero-padded to 100, B=64/GPU, seq_len=20 (T=19), V=10000, dropout on"),
+    "dcnet4": dict(config=0, metric="captions/sec (DCNet XE teacher-forced forward, B=4)",
+                   text="DCNet XE teacher-forced forward (dcnet.py:303-350), B=4, seq_len=20 (T=19), V=10000, eval mode"),
+}
 
 
 def peaks():
@@ -44,6 +65,16 @@ def peaks():
         with open(p) as f:
             return json.load(f), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the forward decode-step kernel per timestep, from the committed
+    ncu capture (profiles/r2_step_traffic.json, written by tools/step_traffic.py); None when absent"""
+    p = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_step")
+    return None
 
 
 class ClockSampler:
@@ -92,103 +123,123 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_step_fn(batch_rows):
-    """the reference's train() body (editnet.py:560-581) on the CPU oracle, all host threads"""
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle)
+def cpu_step_fn(workload, rows):
+    """the reference's own CPU implementation of the workload (oracle port: the reference tree cannot travel to the
+    GPU box), all host threads; returns (step_fn, captions per step, description)"""
     from oracle import editnet_oracle as EO
     from oracle import synth as osynth
     torch.set_num_threads(os.cpu_count() or 1)
+    T = CAPW - 1
+    if workload == "dcnet4":
+        from oracle import dcnet_oracle as DO
+        sd = DO.init_state_dict(V, D, D // 2, D, A, seed=0)
+        b = osynth.make_batch(rows, V, 1, 4, CAPW, PREVW, ragged=False, seed=8)
+
+        def step():
+            with torch.no_grad():
+                DO.xe_forward(sd, b["caps"], b["caplens"], b["prev"], b["prev_len"])
+        return step, rows, "teacher-forced forward, eval mode"
     sd = EO.init_state_dict(V, D, D, D, A, FD, seed=0)
     keys = list(sd.keys())
     params = [sd[k].requires_grad_(True) for k in keys]
     m = [torch.zeros_like(p) for p in params]
     v = [torch.zeros_like(p) for p in params]
-    b = osynth.make_batch(batch_rows, V, R, FD, CAPW, PREVW, ragged=False, seed=0)
     state = {"step": 0}
+    Rr = 100 if workload == "adaptive" else R
+    b = osynth.make_batch(rows, V, Rr, FD, CAPW, PREVW, ragged=False, seed=0, adaptive=(workload == "adaptive"),
+                          Rmin=10 if workload == "adaptive" else None)
 
-    def step():
-        T = CAPW - 1
-        masks = {"enc": (torch.rand(batch_rows, PREVW, D) < 0.5).float(), "emb": (torch.rand(T, batch_rows, D) < 0.5).float(),
-                 "vis": (torch.rand(T, batch_rows, R, D) < 0.5).float(), "fc": (torch.rand(T, batch_rows, D) < 0.5).float()}
-        preds, caps_sorted, dl, _ = EO.xe_forward(sd, b["feats"], b["caps"], b["caplens"], b["prev"], b["prev_len"], masks)
-        loss = EO.xe_loss(preds, caps_sorted, dl)
+    def masks(Tn):
+        return {"enc": (torch.rand(rows, PREVW, D) < 0.5).float(), "emb": (torch.rand(Tn, rows, D) < 0.5).float(),
+                "vis": (torch.rand(Tn, rows, Rr, D) < 0.5).float(), "fc": (torch.rand(Tn, rows, D) < 0.5).float()}
+
+    def opt_step(loss):
         grads = torch.autograd.grad(loss, params, allow_unused=True)
         grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, params)]
         state["step"] += 1
         with torch.no_grad():
             EO.clip_and_adam(params, grads, m, v, step=state["step"])
-        return float(loss.detach())
 
-    return step
+    if workload in ("xe", "adaptive"):
+        def step():
+            preds, caps_sorted, dl, _ = EO.xe_forward(sd, b["feats"], b["caps"], b["caplens"], b["prev"], b["prev_len"],
+                                                      masks(T), image_mean=b.get("image_mean"))
+            loss = EO.xe_loss(preds, caps_sorted, dl)
+            opt_step(loss)
+            return float(loss.detach())
+        return step, rows, "train mode, fwd + CE + bwd + clip + Adam"
+    if workload == "greedy256":
+        def step():
+            with torch.no_grad():
+                EO.rollout(sd, b["prev"], b["prev_len"], b["feats"], V - 2, V - 1, "greedy")
+        return step, rows, "greedy rollout, eval mode"
+    if workload == "scst":
+        forced = torch.randint(1, V - 4, (rows, 18))
+        reward = torch.randn(rows, 1).repeat(1, 18)
+
+        def step():
+            with torch.no_grad():
+                EO.rollout(sd, b["prev"], b["prev_len"], b["feats"], V - 2, V - 1, "greedy")
+            seq, slp = EO.rollout(sd, b["prev"], b["prev_len"], b["feats"], V - 2, V - 1, "forced", masks=masks(18),
+                                  forced=forced)
+            opt_step(EO.reward_criterion(slp, seq, reward))
+        return step, rows, ("greedy rollout + sampled rollout (replayed tokens: torch.multinomial costs the same) + "
+                            "RewardCriterion + bwd + clip + Adam; rewards synthetic (the CIDEr-D scorer of the reference "
+                            "is a Java-free python package that is not installed)")
+    raise ValueError(workload)
+
+
+def time_cpu(workload, rows, n_timed, n_warm):
+    step, caps, desc = cpu_step_fn(workload, rows)
+    for _ in range(n_warm):
+        step()
+    times = []
+    for _ in range(n_timed):
+        t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return caps / dt, dt, desc
+
+
+CPU_ROWS = {"xe": 64, "adaptive": 64, "greedy256": 256, "scst": 64, "dcnet4": 4}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the
-    reference tree itself cannot travel to the GPU box), all host threads, bounded sample."""
+    """--impl reference: the reference's CPU implementation (oracle port), all host threads, the SAME batch shape as
+    the b200 arm; rank 0 only."""
     if rank != 0:
         return
+    w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    rows = B
-    step = cpu_reference_step_fn(rows)
-    t0 = time.perf_counter(); step(); t1 = time.perf_counter() - t0
-    budget = 150.0
-    total = args.steps + args.warmup
-    if t1 * total > budget:      # shrink the sample so the whole run stays within a few minutes
-        rows = max(4, int(B * budget / (t1 * total)) // 4 * 4)
-        step = cpu_reference_step_fn(rows)
-    for _ in range(max(0, args.warmup - (1 if rows == B else 0))):
-        step()
-    times = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
-    val = rows / (ms / 1e3)
-    sample = "%d-caption batch per step (of the B=64 workload), T=19, train mode, fwd+CE+bwd+clip+Adam" % rows
+    rows = CPU_ROWS[args.workload]
+    val, dt, desc = time_cpu(args.workload, rows, args.steps, args.warmup)
+    sample = "%d timed steps of the full %d-caption batch after %d warm-up: %s" % (args.steps, rows, args.warmup, desc)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "captions/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "EditNet XE train step, B=64/GPU, seq_len=20 (T=19), 36x2048 feats, V=10000",
-                   "reference_arm": "CPU oracle port of editnet.py:479-581 (torch CPU, %d threads)" % cores},
+        "impl": "reference", "metric": w["metric"], "value": val, "unit": "captions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["text"]},
+        "reference_arm": "CPU oracle port of the reference path (torch CPU, %d threads)" % cores,
         "cpu_baseline": {"value": val, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
-def secondary_workloads(dev):
-    """configs[2] (EditNet greedy decode, B=256, max_len 18 as the reference hard-codes) and configs[0]
-    (DCNet teacher-forced forward, B=4), device-resident inputs, CUDA events"""
-    from show_edit_tell_b200 import dcnet, editnet_rl, synth
-    out = {}
-    wm = synth.word_map(V)
+# ------------------------------------------------------------------------------------------------ B200 arm
+def keep_masks(L, seed, Bn, T, Wp, Dn, Rn, dev):
+    """the kernels' own dropout keep-bits as the oracle's mask dict (for the step-1 loss check)"""
+    from show_edit_tell_b200 import _lib
 
-    def timed(fn, n):
-        for _ in range(2):
-            fn()
+    def site(sid, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        out = torch.empty(n, device=dev, dtype=torch.float32)
+        _lib.check(L.set_dropout_keep_mask(C.c_void_p(out.data_ptr()), n, seed, sid, 0, None))
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+        return out.view(*shape).cpu()
 
-    torch.manual_seed(1)
-    dec = editnet_rl.DecoderC(wm, D, D, D, A, FD).to(dev).eval()
-    b = synth.make_batch(256, V, R, FD, CAPW, PREVW, seed=7)
-    feats, prev, prev_len = b["feats"].to(dev), b["prev"].to(dev), b["prev_len"].to(dev)
-    with torch.no_grad():
-        ms = timed(lambda: dec(wm, prev, prev_len, feats, True, False), 5)
-    out["editnet_greedy_decode_B256_maxlen18"] = {"captions_per_s": 256 / (ms / 1e3), "ms": ms}
-    dae = dcnet.DAE(wm, None, D, A, D // 2, D).to(dev).eval()
-    b4 = synth.make_batch(4, V, 1, 4, CAPW, PREVW, seed=8)
-    a4 = [b4[k].to(dev) for k in ("caps", "caplens", "prev", "prev_len")]
-    with torch.no_grad():
-        ms = timed(lambda: dae(*a4), 5)
-    out["dcnet_xe_forward_B4"] = {"captions_per_s": 4 / (ms / 1e3), "ms": ms}
-    del dec, dae
-    torch.cuda.empty_cache()
-    return out
+    return {"enc": site(1, Bn, Wp, Dn), "emb": site(2, T, Bn, Dn), "vis": site(3, T, Bn, Rn, Dn), "fc": site(4, T, Bn, Dn)}
 
 
 def main():
@@ -197,8 +248,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="xe", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")     # (kept for older command lines; extras are gone)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -209,8 +261,8 @@ def main():
         return
 
     import torch.distributed as dist
-    from show_edit_tell_b200 import _lib, editnet, synth
-    from show_edit_tell_b200.train import XETrainer
+    from show_edit_tell_b200 import _lib, ciderd, dcnet, editnet, editnet_adaptive, editnet_rl, synth
+    from show_edit_tell_b200.train import SCSTTrainer, XETrainer
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -218,14 +270,107 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-
-    torch.manual_seed(0)
-    dec = editnet.DecoderC(synth.word_map(V), D, D, D, A, FD).to(dev)
-    trainer = XETrainer(dec, distributed=(world > 1))
-    host = synth.make_batch(B, V, R, FD, CAPW, PREVW, ragged=False, seed=100 + rank, pinned=True)
-    keys = ("feats", "caps", "caplens", "prev", "prev_len")
-    resident = [host[k].to(dev) for k in keys]
+    wl = args.workload
+    w = WORKLOADS[wl]
+    wm = synth.word_map(V)
     stream = torch.cuda.current_stream()
+    torch.manual_seed(0)
+    extra = {}
+
+    # ---- workload set-up: host batch (pinned), resident copy, one step on device tensors, result to read back
+    if wl in ("xe", "adaptive"):
+        cls = editnet.DecoderC if wl == "xe" else editnet_adaptive.DecoderC
+        dec = cls(wm, D, D, D, A, FD).to(dev)
+        trainer = XETrainer(dec, distributed=(world > 1))
+        if wl == "xe":
+            host = synth.make_batch(B, V, R, FD, CAPW, PREVW, ragged=False, seed=100 + rank, pinned=True)
+            keys = KEYS
+            regions = R
+        else:
+            from show_edit_tell_b200 import synth as psynth
+            host = psynth.make_batch(B, V, 100, FD, CAPW, PREVW, ragged=False, seed=100 + rank)
+            g = torch.Generator().manual_seed(7 + rank)
+            nreg = torch.randint(10, 101, (B,), generator=g)
+            for i in range(B):
+                host["feats"][i, int(nreg[i]):] = 0
+            host["image_mean"] = torch.stack([host["feats"][i, :int(nreg[i])].mean(0) for i in range(B)], 0)
+            host = {k: v.pin_memory() for k, v in host.items()}
+            keys = KEYS + ("image_mean",)
+            regions = float(nreg.float().mean())
+        rows_per_step = B
+
+        def run(batch, hostb=None):
+            kw = {"image_mean": batch[5]} if wl == "adaptive" else {}
+            if hostb is not None:       # the loader's host copies of the lengths: no device->host sync in the step
+                kw["host_lengths"] = (hostb[2], hostb[4])
+            return trainer.step(*batch[:5], **kw)
+        T = CAPW - 1
+        steps_per_call, alg_bytes = T, W_REC_TF + B * s_bytes(regions)
+        roof_kernel = ("forward decode step of the teacher-forced loop: persistent kernel (step_kernel.cu: all %d timesteps in "
+                       "one cooperative cluster launch, 7 phases per step behind grid barriers)" % T)
+    elif wl == "greedy256":
+        dec = editnet_rl.DecoderC(wm, D, D, D, A, FD).to(dev).eval()
+        host = synth.make_batch(256, V, R, FD, CAPW, PREVW, seed=7 + rank, pinned=True)
+        keys = ("prev", "prev_len", "feats")
+        rows_per_step = 256
+
+        def run(batch, hostb=None):
+            with torch.no_grad():
+                seq, slp = dec(wm, batch[0], batch[1], batch[2], True, False)
+            return seq
+        steps_per_call, alg_bytes = 18, W_REC_AR + 256 * s_bytes(R, True)
+        roof_kernel = "autoregressive decode step (launch chain: embedding, word projections, step GEMMs + cells, attention, fc, sampler)"
+    elif wl == "scst":
+        dec = editnet_rl.DecoderC(wm, D, D, D, A, FD).to(dev)
+        trainer = SCSTTrainer(dec, distributed=(world > 1))
+        host = synth.make_batch(B, V, R, FD, CAPW, PREVW, seed=100 + rank, pinned=True)
+        g = torch.Generator().manual_seed(3 + rank)
+        # 5 references per image in the loader's layout (<start> words <end> pads, width 52), editnet_rl.py:660-673
+        allcaps = torch.zeros(B, 5, 52, dtype=torch.long)
+        for i in range(B):
+            for r in range(5):
+                n = int(torch.randint(6, 16, (1,), generator=g))
+                allcaps[i, r, 0] = V - 2
+                allcaps[i, r, 1:1 + n] = torch.randint(1, V - 3, (n,), generator=g)
+                allcaps[i, r, 1 + n] = V - 1
+        host["allcaps"] = allcaps.pin_memory()
+        df = {}
+        for i in range(B):      # document frequencies of the synthetic references (preprocess_rl.py:7-55 format)
+            seen = set()
+            for r in range(5):
+                toks = [int(x) for x in allcaps[i, r, 1:] if int(x) not in (0, V - 2)]
+                toks = [0 if x == V - 1 else x for x in toks]
+                for n in range(1, 5):
+                    for k in range(len(toks) - n + 1):
+                        seen.add(tuple(toks[k:k + n]))
+            for ng in seen:
+                df[ng] = df.get(ng, 0) + 1
+        table = ciderd.CiderDTable(df, float(B), dev)
+        keys = ("feats", "prev", "prev_len", "allcaps")
+        rows_per_step = B
+
+        def run(batch, hostb=None):
+            return trainer.step(wm, batch[0], batch[1], batch[2],
+                                lambda s, gseq: ciderd.self_critical_reward(s, gseq, batch[3], wm, table))
+        steps_per_call, alg_bytes = 36, W_REC_AR + B * s_bytes(R, True)
+        roof_kernel = ("autoregressive decode steps of the two rollouts (2 x 18); the reverse pass, reward and optimizer "
+                       "are inside the timed step, so this fraction is a lower bound")
+    else:   # dcnet4
+        dec = dcnet.DAE(wm, None, D, A, D // 2, D).to(dev).eval()
+        host = synth.make_batch(4, V, 1, 4, CAPW, PREVW, seed=8, pinned=True)
+        keys = ("caps", "caplens", "prev", "prev_len")
+        rows_per_step = 4
+
+        def run(batch, hostb=None):
+            with torch.no_grad():
+                return dec(*batch)[0]
+        T = CAPW - 1
+        # recurrent weights of one DCNet step (dcnet.py:336-348): attention_lstm h2 + hh parts, cap_decoder_att, language_lstm
+        steps_per_call, alg_bytes = T, 4 * (4 * D * D * 2 + A * D + 4 * D * 2 * D + 4 * D * D) + 4 * (18 * D * 4 + 18 * A * 4)
+        roof_kernel = "DCNet decode step (launch chain); B=4 is latency-bound by construction"
+
+    resident = [host[k].to(dev) for k in keys]
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
 
     def barrier():
         if world > 1:
@@ -245,42 +390,59 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
-    def step_resident():
-        trainer.step(*resident)
-
     # End to end through the public API: every step's inputs start in pinned host memory (feed.DevicePrefetcher copies
-    # batch i+1 host->device on a copy stream while step i computes) and its loss ends on the host (copied to pinned
-    # memory behind its step, read one step later).  All copies of the timed steps are inside the timed region.
+    # batch i+1 host->device on a copy stream while step i computes) and its result (loss / token ids) ends on the host
+    # (copied to pinned memory behind its step, read one step later).  All copies sit inside the timed region.
     from show_edit_tell_b200.feed import DevicePrefetcher
-    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    probe = run(resident)
+    d2h = probe.numel() * probe.element_size()
+    res_host = [torch.zeros(probe.shape, dtype=probe.dtype).pin_memory() for _ in range(2)]
+    res_ev = [torch.cuda.Event() for _ in range(2)]
 
     def run_e2e(n_steps):
-        last = None
         feed_iter = DevicePrefetcher((tuple(host[k] for k in keys) for _ in range(n_steps)), dev)
-        for i, batch in enumerate(feed_iter):
+        for i, batch in enumerate(iter(feed_iter)):
             slot = i % 2
-            loss = trainer.step(*batch)
-            loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
-            loss_ev[slot].record(stream)
-            if i > 0:                                       # device->host read of the previous step's result
-                loss_ev[1 - slot].synchronize()
-                last = float(loss_host[1 - slot])
-        if n_steps > 0:                                     # the last loss is on the host before the clock stops
-            loss_ev[(n_steps - 1) % 2].synchronize()
-            last = float(loss_host[(n_steps - 1) % 2])
-        return last
+            out = run(batch, feed_iter.host_batch)
+            res_host[slot].copy_(out.detach().reshape(res_host[slot].shape), non_blocking=True)
+            res_ev[slot].record(stream)
+            if i > 0:
+                res_ev[1 - slot].synchronize()
+        if n_steps > 0:
+            res_ev[(n_steps - 1) % 2].synchronize()
+
+    # ---- step-1 check against the oracle (headline workload, single GPU): same weights, same batch, the kernels' own
+    # dropout bits -> |loss - oracle loss|
+    loss_err = None
+    if wl == "xe" and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import editnet_oracle as EO
+        sd = {k: v.detach().cpu().clone() for k, v in dec.state_dict().items() if not k.startswith("caption_encoder.embed.")}
+        seed = 20261017
+        saved_lr, trainer.lr = trainer.lr, 0.0
+        loss1 = float(trainer.step(*resident, seed=seed))
+        trainer.lr = saved_lr
+        trainer.step_count = 0
+        trainer._state["m"].zero_(); trainer._state["v"].zero_()
+        mk = keep_masks(L, seed, B, CAPW - 1, PREVW, D, R, dev)
+        with torch.no_grad():
+            preds, caps_sorted, dl, _ = EO.xe_forward(sd, host["feats"], host["caps"], host["caplens"], host["prev"],
+                                                      host["prev_len"], mk, stable_sort=True)
+            loss_err = abs(loss1 - float(EO.xe_loss(preds, caps_sorted, dl)))
+        del mk, preds
 
     for _ in range(args.warmup):
-        step_resident()
+        run(resident)
     L.set_profile_enable(1)
     L.set_launch_count(1)
+    la, st = C.c_longlong(), C.c_longlong()
+    L.set_step_stats(C.byref(la), C.byref(st), 1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(step_resident, args.steps)
+    ms = timed(lambda: run(resident), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(L.set_launch_count(1)) // args.steps
+    L.set_step_stats(C.byref(la), C.byref(st), 1)
     fwd_ms, bwd_ms = C.c_float(), C.c_float()
     L.set_profile_read(C.byref(fwd_ms), C.byref(bwd_ms))
     L.set_profile_enable(0)
@@ -297,47 +459,46 @@ def main():
     ms_e2e = float(ms_t) / args.steps
 
     pk, pk_src = peaks()
-    T = CAPW - 1
-    step_us = fwd_ms.value / T * 1e3
-    achieved = step_bytes(B) / (fwd_ms.value / T * 1e-3) / 1e9
-    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
-    # secondary workloads of BASELINE.json (parity-test cases, reported for context only)
-    extras = {}
-    if rank == 0 and not args.no_extras:
-        extras = secondary_workloads(dev)
+    if wl in ("xe", "adaptive") and fwd_ms.value > 0:
+        # the forward loop is timed by CUDA events inside the library, on the launch stream
+        step_us = fwd_ms.value / steps_per_call * 1e3
+        timing = "CUDA events around the %d-step forward loop inside the library" % steps_per_call
+    else:
+        step_us = ms / steps_per_call * 1e3
+        timing = "whole call / %d decode steps (prologue, reward, reverse pass included: lower bound)" % steps_per_call
+    achieved = alg_bytes / (step_us * 1e-6) / 1e9
     line = {
-        "metric": METRIC, "value": world * B / (ms / 1e3), "unit": "captions/s", "n_gpus": world,
+        "metric": w["metric"], "value": world * rows_per_step / (ms / 1e3), "unit": "captions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "EditNet XE train step (fwd + packed CE + bwd + clip 0.25 + Adam), B=64/GPU, "
-                               "seq_len=20 (T=19), 36x2048 feats, V=10000, dropout on",
-                   "global_batch": world * B, "parallelism": "dp%d" % world,
-                   "l2": "per-step working set (355 MB weights + ~0.7 GB activations) exceeds the 126 MB L2; no flush"},
+        "config": {"workload": w["text"], "baseline_config": w["config"], "global_batch": world * rows_per_step,
+                   "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (355 MB weights + activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
-        "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "captions/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "pipeline": "feed.DevicePrefetcher: H2D of batch i+1 on a copy stream while step i computes; loss "
-                            "read back one step behind"},
+        "e2e": {"value": world * rows_per_step / (ms_e2e / 1e3), "unit": "captions/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "pipeline": "feed.DevicePrefetcher: H2D of batch i+1 on a copy stream while step i computes; result "
+                            "read back one step behind; caption lengths taken from the loader's host tensors (no "
+                            "device->host sync inside the step)"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "decode step, forward (launch chain of one timestep: 5 tcgen05 GEMM launches with "
-                                               "the LSTM / copy-LSTM cells fused in their cluster epilogues + attention + "
-                                               "context gate; programmatic dependent launch between them)",
-                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     # DRAM bytes of the 7 launches of one forward step, summed from the committed ncu capture
-                     # profiles/r1_step_kernels_final.md (dram__bytes_read.sum + dram__bytes_write.sum)
-                     "traffic": 188.8e6, "algorithmic_bytes_per_step": step_bytes(B), "us_per_step": step_us,
-                     "bwd_us_per_step": bwd_ms.value / T * 1e3, "peak_source": pk_src},
+        "persistent_step_kernel": {"launches_per_step": la.value / args.steps, "timesteps_per_step": st.value / args.steps},
+        "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"],
+                     "traffic": measured_traffic() if wl == "xe" else None,
+                     "algorithmic_bytes_per_step": alg_bytes, "us_per_step": step_us, "timing": timing,
+                     "bwd_us_per_step": (bwd_ms.value / steps_per_call * 1e3) if bwd_ms.value > 0 else None,
+                     "peak_source": pk_src},
     }
+    if loss_err is not None:
+        line["loss_abs_err_vs_oracle"] = loss_err
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        step = cpu_reference_step_fn(B)
-        step()
-        t0 = time.perf_counter(); step(); step(); dt = (time.perf_counter() - t0) / 2
-        line["cpu_baseline"] = {"value": B / dt, "unit": "captions/s", "cores": cores, "kind": "port",
-                                "sample": "2 timed full B=64 train steps (T=19) after 1 warm-up, oracle port, "
-                                          "torch CPU with %d threads" % cores}
-    if extras:
-        line["extras"] = extras
+        rows = CPU_ROWS[wl]
+        n_timed = 2 if wl != "dcnet4" else 10
+        val, dt, desc = time_cpu(wl, rows, n_timed, 1)
+        line["cpu_baseline"] = {"value": val, "unit": "captions/s", "cores": cores, "kind": "port",
+                                "sample": "%d timed steps of the full %d-caption batch after 1 warm-up, oracle port, torch "
+                                          "CPU with %d threads: %s" % (n_timed, rows, cores, desc)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -294,6 +294,12 @@ SET_API int set_gemm_trace(void* buf);
    [2100 + 8k + s] SM-clock stamps of K-block k of CTA 0 */
 SET_API int set_gemm_trace_seq(void* buf, long stride_u64, int launches);
 SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
+/* Data-parallel overlap (new: the reference is single-process).  Arms the NEXT set_editnet_xe_backward /
+ * set_editnet_rollout_backward call of this thread: when the gradients of attention_lstm.*, copy_lstm.* and fc.* -- the
+ * contiguous tail of the flat parameter buffer in EDITNET_FIELDS order, from attention_lstm.weight_ih on -- are final
+ * (about two thirds into the reverse pass), the call records an event on its stream and makes `comm_stream` wait for
+ * it.  An all-reduce of that tail enqueued on `comm_stream` after the call returns overlaps the rest of the pass. */
+SET_API int set_backward_bucket_notify(void* comm_stream);
 /* persistent decode-step kernel (csrc/step_kernel.cu): launches since the last reset and the timesteps they covered
    (0 launches: the shape fell outside the persistent path and the per-step launch chain ran) */
 SET_API int set_step_stats(long long* launches, long long* steps, int reset);

@@ -179,6 +179,7 @@ _SIGS = {
     "set_gemm_trace_seq": (C.c_int, [_P, C.c_long, C.c_int]),
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm_twin_launches": (C.c_longlong, [C.c_int]),
+    "set_backward_bucket_notify": (C.c_int, [_P]),
     "set_step_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_step_trace": (C.c_int, [_P]),
     "set_step_geometry": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -587,6 +587,26 @@ int steps_persistent(Ctx& c, const float* feats, int t0, int nt, const int* bt, 
 }
 
 // ------------------------------------------------------------------------ reverse pass
+// Data-parallel overlap: the gradients of attention_lstm, copy_lstm and fc -- the contiguous tail of the flat parameter
+// buffer, 234 of 355 MB -- are final about two thirds of the way through the reverse pass (before the visual feature
+// path and the encoder BPTT).  When armed (set_backward_bucket_notify), backward_core records an event at that point
+// and makes the caller's communication stream wait for it: an all-reduce of the tail enqueued on that stream right
+// after the backward call returns then runs underneath the rest of the reverse pass.
+thread_local cudaStream_t g_bucket_stream = nullptr;
+thread_local bool g_bucket_armed = false;
+int bucket_notify(cudaStream_t st) {
+  if (!g_bucket_armed) return SET_OK;
+  g_bucket_armed = false;
+  static thread_local cudaEvent_t ev[64] = {nullptr};
+  int dev = 0;
+  SET_CHECK_CUDA(cudaGetDevice(&dev));
+  SET_REQUIRE(dev >= 0 && dev < 64, "device ordinal");
+  if (!ev[dev]) SET_CHECK_CUDA(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
+  SET_CHECK_CUDA(cudaEventRecord(ev[dev], st));
+  SET_CHECK_CUDA(cudaStreamWaitEvent(g_bucket_stream, ev[dev], 0));
+  return SET_OK;
+}
+
 struct DLogits {
   const float* p; long ld; int inner; long ld_inner; const int* row_len;  // rows are time-major m = t*B + i
 };
@@ -859,6 +879,8 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
         {s.dK, (long)D, TB, D, g.cl_gcm_b, 0, 0},           {s.datt1c, (long)A, B * P, A, g.ca_feat_b, 0, 0}};
     SET_PROPAGATE(colsum_batch(cj, (int)(sizeof(cj) / sizeof(cj[0])), st));
   }
+  // attention_lstm.*, copy_lstm.*, fc.* (the tail of the flat gradient buffer) are final from here on
+  SET_PROPAGATE(bucket_notify(st));
   {  // d prev_h also flows through cap_features_att
     GemmProblem p = gemm_problem(B * P, D, s.dprev_h, D);
     dx(p, s.datt1c, A, w.ca_feat_w, s.t_ca_feat, A, D, 0);
@@ -1295,6 +1317,12 @@ int set_step_stats(long long* launches, long long* steps, int reset) {
   if (launches) *launches = g_step_launches;
   if (steps) *steps = g_step_steps;
   if (reset) g_step_launches = g_step_steps = 0;
+  return SET_OK;
+}
+
+int set_backward_bucket_notify(void* comm_stream) {
+  g_bucket_stream = reinterpret_cast<cudaStream_t>(comm_stream);
+  g_bucket_armed = true;
   return SET_OK;
 }
 

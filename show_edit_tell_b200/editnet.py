@@ -257,17 +257,26 @@ class EditNetBase(nn.Module):
 
     # ---- teacher-forced path -------------------------------------------------------------
     def _prepare_xe(self, image_features, image_mean, encoded_captions, caption_lengths,
-                    encoded_previous_captions, previous_cap_length, seed=None):
+                    encoded_previous_captions, previous_cap_length, seed=None, host_lengths=None):
+        """`host_lengths = (caption_lengths, previous_cap_length)` as CPU tensors (the loader has them on the host
+        anyway) spares the device->host read of the lengths, i.e. the one host sync of a step."""
         self._require_cuda(image_features)
         self.flatten_parameters()
-        lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True, stable=True)  # editnet.py:488 (stable: ties as on CPU)
+        if host_lengths is not None:
+            lens_h, sort_h = host_lengths[0].reshape(-1).sort(dim=0, descending=True, stable=True)
+            sort_ind = sort_h.to(image_features.device, non_blocking=True)
+            host = (lens_h - 1).tolist() + [int(host_lengths[1].max())]
+        else:
+            lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True, stable=True)  # editnet.py:488 (stable: ties as on CPU)
+            host = None
         call = _Call()
         call.feats = image_features[sort_ind].contiguous().float()
         call.image_mean = None if image_mean is None else image_mean[sort_ind].contiguous().float()
         call.caps = encoded_captions[sort_ind].contiguous()
         call.prev = encoded_previous_captions[sort_ind].contiguous()
         call.prev_len = previous_cap_length[sort_ind].contiguous().view(-1)
-        host = torch.cat([lens - 1, call.prev_len.max().view(1)]).tolist()                # one D2H sync
+        if host is None:
+            host = torch.cat([lens - 1, call.prev_len.max().view(1)]).tolist()            # one D2H sync
         call.decode_lengths = host[:-1]
         P = int(host[-1])
         B, Wc = call.caps.shape

@@ -112,17 +112,18 @@ class DevicePrefetcher:
     def __init__(self, loader, device):
         self.loader = loader
         self.device = torch.device(device)
+        self.host_batch = None      # the host tensors of the batch handed out last (lengths stay useful on the host)
         self.cuda = self.device.type == "cuda"
         self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
 
     def _stage(self, batch):
         if not self.cuda:
-            return tuple(batch), None
+            return tuple(batch), None, tuple(batch)
         with torch.cuda.stream(self.stream):
             dev = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return dev, ev
+        return dev, ev, tuple(batch)
 
     def __iter__(self):
         it = iter(self.loader)
@@ -131,7 +132,7 @@ class DevicePrefetcher:
         except StopIteration:
             return
         while nxt is not None:
-            cur, ev = nxt
+            cur, ev, self.host_batch = nxt
             try:
                 nxt = self._stage(next(it))            # enqueue the next copy before handing out the current batch
             except StopIteration:

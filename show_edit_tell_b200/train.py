@@ -27,14 +27,41 @@ from .parallel import allreduce_sums
 
 class XETrainer:
     def __init__(self, decoder, lr=5e-4, max_norm=0.25, betas=(0.9, 0.999), eps=1e-8, process_group=None,
-                 distributed=None):
+                 distributed=None, overlap=True):
         self.decoder = decoder
         self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
         self.distributed = dist.is_initialized() if distributed is None else distributed
         self.group = process_group
+        self.overlap = overlap          # DP: all-reduce the early-final tail of the gradients under the reverse pass
         self.step_count = 0
         self._state = None
+        self._comm_stream = None
         self.gpu_launches_last_step = 0
+
+    def _tail_offset(self):
+        """first element of the gradient tail that is final early in the reverse pass (attention_lstm.weight_ih on)"""
+        names = [n for n, _ in self.decoder.FIELDS]
+        return self.decoder._offsets[names.index("al_wih")]
+
+    def _allreduce_overlapped(self, grad, n, local_count, run_backward):
+        """run_backward() enqueues the reverse pass; the tail bucket (+ the count slot behind it) is all-reduced on a
+        side stream as soon as it is final, the head bucket after the pass.  Returns the count slot."""
+        main = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=grad.device)
+        comm = self._comm_stream
+        off = self._tail_offset()
+        count_slot = grad[n:n + 1]
+        count_slot.copy_(local_count.reshape(1).to(count_slot.dtype))
+        check(_lib.lib().set_backward_bucket_notify(C.c_void_p(comm.cuda_stream)))
+        run_backward()                                   # (records the event + makes `comm` wait, mid-pass)
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi:
+            with torch.cuda.stream(comm):
+                dist.all_reduce(grad[off:n + 64], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(grad[:off], op=dist.ReduceOp.SUM, group=self.group)
+            main.wait_stream(comm)
+        return count_slot
 
     def _ensure_state(self):
         flat = self.decoder.flatten_parameters()
@@ -74,15 +101,16 @@ class XETrainer:
         self.max_norm = sd.get("max_norm", self.max_norm)
 
     def step(self, image_features, encoded_captions, caption_lengths, encoded_previous_captions,
-             previous_cap_length, image_mean=None, seed=None):
-        """one optimisation step; returns the (device) mean loss of this rank's shard"""
+             previous_cap_length, image_mean=None, seed=None, host_lengths=None):
+        """one optimisation step; returns the (device) mean loss of this rank's shard.  With `host_lengths` =
+        (caption_lengths, previous_cap_length) as CPU tensors the step never synchronises with the host."""
         dec = self.decoder
         dec.train()
         flat, st = self._ensure_state()
         if image_features.shape[0] == 0:
             return self._empty_shard_step(flat, st)
         call = dec._prepare_xe(image_features, image_mean, encoded_captions, caption_lengths,
-                               encoded_previous_captions, previous_cap_length, seed=seed)
+                               encoded_previous_captions, previous_cap_length, seed=seed, host_lengths=host_lengths)
         L = _lib.lib()
         s = call.shape
         # logits stay time-major inside the workspace; the loss kernel turns them into d logits in place
@@ -96,13 +124,20 @@ class XETrainer:
         grad = st["grad"]
         grad.zero_()
         g = dec._struct_for(grad[:st["n"]])
-        check(L.set_editnet_xe_backward(
-            C.byref(call.dims), C.byref(s), C.byref(dec._struct), C.byref(g), ptr(call.feats), ptr(call.caps),
-            call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, None, ptr(call.ws), call.ws.numel(),
-            _stream()))
+
+        def run_backward():
+            check(L.set_editnet_xe_backward(
+                C.byref(call.dims), C.byref(s), C.byref(dec._struct), C.byref(g), ptr(call.feats), ptr(call.caps),
+                call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, None, ptr(call.ws), call.ws.numel(),
+                _stream()))
+
         count_dev = None
-        if self.distributed:
-            count_dev = allreduce_sums(grad, st["n"], st["loss"][1], self.group)
+        if self.distributed and self.overlap:
+            count_dev = self._allreduce_overlapped(grad, st["n"], st["loss"][1], run_backward)
+        else:
+            run_backward()
+            if self.distributed:
+                count_dev = allreduce_sums(grad, st["n"], st["loss"][1], self.group)
         self.step_count += 1
         check(_lib.lib().set_clip_adam(ptr(flat), ptr(grad), ptr(st["m"]), ptr(st["v"]), st["n"], self.step_count,
                                        self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0,
