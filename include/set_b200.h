@@ -294,11 +294,48 @@ SET_API int set_gemm_trace(void* buf);
    [2100 + 8k + s] SM-clock stamps of K-block k of CTA 0 */
 SET_API int set_gemm_trace_seq(void* buf, long stride_u64, int launches);
 SET_API int set_gemm_stats(long long* tc_launches, long long* simt_launches, int reset);
+/* ---- Sub-module call surface: the reference's beam searches call the decoder's sub-modules one by one
+ * (evaluate(), editnet.py:613,645-653; evaluate_full(), eval/eval xe/eval_full.py:107-149).  Each entry point is one
+ * of those forwards exactly as the reference computes it (nothing hoisted), inference only, on contiguous fp32 / int64
+ * device buffers; scratch comes from the caller (size queries below, in floats). */
+/* EmbeddingC.forward, editnet.py:300-304: out[n][D] = dropout(relu(table[tokens[n]])) */
+SET_API int set_embed_forward(const int64_t* tokens, long n, const float* table, int V, int D, int train, uint64_t seed,
+                              float* out, void* stream);
+/* nn.LSTMCell.forward (attention_lstm, editnet.py:532; DCNet cells dcnet.py:338,346): x [rows][I], gates_scratch [rows][4D] */
+SET_API int set_lstm_cell_forward(int rows, int I, int D, const float* x, const float* h, const float* c,
+                                  const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                  float* gates_scratch, float* h_out, float* c_out, void* stream);
+/* CaptionAttentionC.forward, editnet.py:364-381: prev_h [rows][P][D], h1 / emb [rows][D], mask [rows][P] ->
+ * out [rows][D] (gated context), alpha [rows][P] */
+SET_API size_t set_caption_attention_scratch_floats(const SetDims* dims, int rows, int P);
+SET_API int set_caption_attention_forward(const SetDims* dims, int rows, int P, const SetEditNetParams* w,
+                                          const float* prev_h, const float* h1, const float* emb, const float* mask,
+                                          float* scratch, size_t scratch_floats, float* out, float* alpha, void* stream);
+/* VisualAttentionC.forward, editnet.py:439-447 (adaptive: editnet_adaptive.py:438-457): feats [rows][R][F], h1 [rows][D]
+ * -> out [rows][F]; att_embed is recomputed on every call, as the reference does */
+SET_API size_t set_visual_attention_scratch_floats(const SetDims* dims, int rows, int R);
+SET_API int set_visual_attention_forward(const SetDims* dims, int rows, int R, const SetEditNetParams* w,
+                                         const float* feats, const float* h1, int adaptive, int train, uint64_t seed,
+                                         float* scratch, size_t scratch_floats, float* out, void* stream);
+/* DCNet CaptionAttention.forward, dcnet.py:254-270: enc [rows][P][D], h1 [rows][D], mask [rows][P] -> out [rows][D] */
+SET_API size_t set_dcnet_caption_attention_scratch_floats(const SetDims* dims, int rows, int P);
+SET_API int set_dcnet_caption_attention_forward(const SetDims* dims, int rows, int P, const SetDcNetParams* w,
+                                                const float* enc, const float* h1, const float* mask, float* scratch,
+                                                size_t scratch_floats, float* out, void* stream);
+/* SelectC.forward, editnet.py:403-421: prev_m [rows][P][D], alpha [rows][P] -> out [rows][D] */
+SET_API int set_select_forward(int rows, int P, int D, const float* prev_m, const float* alpha, float* out, void* stream);
+/* CopyLSTMCellC.forward, editnet.py:265-285: x [rows][2D+F], h / c / mem [rows][D] -> h_out, c_out */
+SET_API size_t set_copy_lstm_scratch_floats(const SetDims* dims, int rows);
+SET_API int set_copy_lstm_forward(const SetDims* dims, int rows, const SetEditNetParams* w, const float* x,
+                                  const float* h, const float* c, const float* mem, float* scratch,
+                                  size_t scratch_floats, float* h_out, float* c_out, void* stream);
+
 /* Data-parallel overlap (new: the reference is single-process).  Arms the NEXT set_editnet_xe_backward /
- * set_editnet_rollout_backward call of this thread: when the gradients of attention_lstm.*, copy_lstm.* and fc.* -- the
- * contiguous tail of the flat parameter buffer in EDITNET_FIELDS order, from attention_lstm.weight_ih on -- are final
- * (about two thirds into the reverse pass), the call records an event on its stream and makes `comm_stream` wait for
- * it.  An all-reduce of that tail enqueued on `comm_stream` after the call returns overlaps the rest of the pass. */
+ * set_editnet_rollout_backward call of this thread: when every parameter gradient except those of embed.*,
+ * caption_encoder.* and visual_attention.att_embed / features_att is final (about two thirds into the reverse pass:
+ * before the visual feature path and the encoder BPTT), the call records an event on its stream and makes `comm_stream`
+ * wait for it.  An all-reduce of those gradients enqueued on `comm_stream` after the call returns overlaps the rest of
+ * the pass (the Python side keeps them contiguous in its flat buffer). */
 SET_API int set_backward_bucket_notify(void* comm_stream);
 /* persistent decode-step kernel (csrc/step_kernel.cu): launches since the last reset and the timesteps they covered
    (0 launches: the shape fell outside the persistent path and the per-step launch chain ran) */

@@ -109,6 +109,32 @@ def eval_full_search(device="cpu"):
     return ns["evaluate_full"]
 
 
+def editnet_evaluate_search(device="cpu"):
+    """The reference's own beam search, `evaluate` of editnet.py:595-719, as a callable
+    `(loader, decoder, beam_size, epoch, vocab_size, word_map) -> results`; same two edits as eval_full_search (the `/`
+    of :666 becomes `//`, the COCO scoring tail behind the per-image loop is cut)."""
+    path = os.path.join(REFERENCE_ROOT, "editnet.py")
+    with open(path, "r") as f:
+        tree = ast.parse(f.read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "evaluate"][0]
+    loop_at = max(i for i, n in enumerate(fn.body) if isinstance(n, ast.For))
+    fn.body = fn.body[:loop_at + 1] + [ast.Return(value=ast.Name(id="results", ctx=ast.Load()))]
+
+    class FloorDiv(ast.NodeTransformer):
+        def visit_Assign(self, node):
+            self.generic_visit(node)
+            t = node.targets[0]
+            if isinstance(t, ast.Name) and t.id == "prev_word_inds" and isinstance(node.value, ast.BinOp) \
+                    and isinstance(node.value.op, ast.Div):
+                node.value.op = ast.FloorDiv()
+            return node
+
+    fn = ast.fix_missing_locations(FloorDiv().visit(fn))
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "device": torch.device(device), "tqdm": lambda it, **kw: it}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["evaluate"]
+
+
 def eval_class_modules():
     """the class-only copies the eval scripts import (`from dae import *; from editnet import *`, eval_full.py:18-19)"""
     e = extract_classes(os.path.join("eval", "eval xe", "editnet.py"), EDITNET_CLASSES)

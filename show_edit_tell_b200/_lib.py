@@ -180,6 +180,21 @@ _SIGS = {
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm_twin_launches": (C.c_longlong, [C.c_int]),
     "set_backward_bucket_notify": (C.c_int, [_P]),
+    "set_embed_forward": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P]),
+    "set_lstm_cell_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "set_caption_attention_scratch_floats": (C.c_size_t, [C.POINTER(SetDims), C.c_int, C.c_int]),
+    "set_caption_attention_forward": (C.c_int, [C.POINTER(SetDims), C.c_int, C.c_int, C.POINTER(SetEditNetParams), _P, _P, _P,
+                                                _P, _P, C.c_size_t, _P, _P, _P]),
+    "set_visual_attention_scratch_floats": (C.c_size_t, [C.POINTER(SetDims), C.c_int, C.c_int]),
+    "set_visual_attention_forward": (C.c_int, [C.POINTER(SetDims), C.c_int, C.c_int, C.POINTER(SetEditNetParams), _P, _P,
+                                               C.c_int, C.c_int, C.c_uint64, _P, C.c_size_t, _P, _P]),
+    "set_dcnet_caption_attention_scratch_floats": (C.c_size_t, [C.POINTER(SetDims), C.c_int, C.c_int]),
+    "set_dcnet_caption_attention_forward": (C.c_int, [C.POINTER(SetDims), C.c_int, C.c_int, C.POINTER(SetDcNetParams), _P, _P,
+                                                      _P, _P, C.c_size_t, _P, _P]),
+    "set_select_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "set_copy_lstm_scratch_floats": (C.c_size_t, [C.POINTER(SetDims), C.c_int]),
+    "set_copy_lstm_forward": (C.c_int, [C.POINTER(SetDims), C.c_int, C.POINTER(SetEditNetParams), _P, _P, _P, _P, _P,
+                                        C.c_size_t, _P, _P, _P]),
     "set_step_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_step_trace": (C.c_int, [_P]),
     "set_step_geometry": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -587,9 +587,9 @@ int steps_persistent(Ctx& c, const float* feats, int t0, int nt, const int* bt, 
 }
 
 // ------------------------------------------------------------------------ reverse pass
-// Data-parallel overlap: the gradients of attention_lstm, copy_lstm and fc -- the contiguous tail of the flat parameter
-// buffer, 234 of 355 MB -- are final about two thirds of the way through the reverse pass (before the visual feature
-// path and the encoder BPTT).  When armed (set_backward_bucket_notify), backward_core records an event at that point
+// Data-parallel overlap: every parameter gradient except those of the embedding table, the caption encoder and
+// att_embed / features_att -- 265 of 355 MB, laid out as one contiguous range by the Python side -- is final about two
+// thirds of the way through the reverse pass (before the visual feature path and the encoder BPTT).  When armed (set_backward_bucket_notify), backward_core records an event at that point
 // and makes the caller's communication stream wait for it: an all-reduce of the tail enqueued on that stream right
 // after the backward call returns then runs underneath the rest of the reverse pass.
 thread_local cudaStream_t g_bucket_stream = nullptr;
@@ -879,7 +879,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
         {s.dK, (long)D, TB, D, g.cl_gcm_b, 0, 0},           {s.datt1c, (long)A, B * P, A, g.ca_feat_b, 0, 0}};
     SET_PROPAGATE(colsum_batch(cj, (int)(sizeof(cj) / sizeof(cj[0])), st));
   }
-  // attention_lstm.*, copy_lstm.*, fc.* (the tail of the flat gradient buffer) are final from here on
+  // final from here on: everything but embed.*, caption_encoder.*, visual_attention.att_embed / features_att
   SET_PROPAGATE(bucket_notify(st));
   {  // d prev_h also flows through cap_features_att
     GemmProblem p = gemm_problem(B * P, D, s.dprev_h, D);

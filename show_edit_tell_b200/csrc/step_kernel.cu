@@ -129,7 +129,6 @@ __device__ __forceinline__ float tanh_(float x) {
   return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * xc));
 }
 
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldcg2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
 
 }  // namespace

@@ -8,7 +8,9 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import DCNET_FIELDS, SetDcNetParams, SetDims, SetSeqShape, check, ptr
-from .editnet import EditNetBase, _Call, _draw_seed, _stream
+import weakref
+
+from .editnet import EditNetBase, EmbeddingC, LinearK, LSTMCellK, _c, _Call, _draw_seed, _Owned, _stream
 
 
 class Embedding(nn.Module):
@@ -26,9 +28,11 @@ class Embedding(nn.Module):
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(0.5)
 
+    forward = EmbeddingC.forward     # dropout(relu(Emb[x])), dcnet.py:199-206
 
-class CaptionEncoder(nn.Module):
-    """dcnet.py:209-243"""
+
+class CaptionEncoder(_Owned, nn.Module):
+    """dcnet.py:209-243; forward(src, src_len) -> (outputs (B,P',2C), final_hidden (B,2C), mask (B,P')) as :220-243"""
 
     def __init__(self, vocab_size, emb_dim, enc_hid_dim, concat_output_dim, embed):
         super().__init__()
@@ -39,15 +43,40 @@ class CaptionEncoder(nn.Module):
         self.lstm_encoder = nn.LSTM(emb_dim, enc_hid_dim, batch_first=True, bidirectional=True)
         self.concat = nn.Linear(enc_hid_dim * 2, concat_output_dim)
 
+    def forward(self, src, src_len):
+        dae = self._dec()
+        sess = dae.step_session(src, src_len)        # runs the bi-LSTM encoder into the session workspace
+        B, P, D = sess.shape.B, sess.shape.P, dae.decoder_dim
 
-class CaptionAttention(nn.Module):
-    """dcnet.py:245-270"""
+        def buf(name):
+            off, nbytes = C.c_size_t(), C.c_size_t()
+            check(_lib.lib().set_dcnet_workspace_lookup(C.byref(sess.dims), C.byref(sess.shape), name.encode(),
+                                                        C.byref(off), C.byref(nbytes)))
+            return sess.ws[off.value:off.value + nbytes.value].view(torch.float32)
+
+        return (buf("enc_out").view(B, P, D).clone(), buf("final_hidden").view(B, D).clone(), buf("mask").view(B, P).clone())
+
+
+class CaptionAttention(_Owned, nn.Module):
+    """dcnet.py:245-270; forward(enc, h1, mask) -> context as :254-270"""
 
     def __init__(self, caption_features_dim, decoder_dim, attention_dim):
         super().__init__()
         self.cap_features_att = nn.Linear(caption_features_dim * 2, attention_dim)
         self.cap_decoder_att = nn.Linear(decoder_dim, attention_dim)
         self.cap_full_att = nn.Linear(attention_dim, 1)
+
+    def forward(self, prev_cap_features, decoder_hidden, prev_cap_mask):
+        dae = self._dec()
+        enc, h1, mask = _c(prev_cap_features), _c(decoder_hidden), _c(prev_cap_mask)
+        rows, P = enc.shape[0], enc.shape[1]
+        dims = dae._dims()
+        n = _lib.lib().set_dcnet_caption_attention_scratch_floats(C.byref(dims), rows, P)
+        scratch = torch.empty(n, device=enc.device)
+        out = torch.empty(rows, dae.decoder_dim, device=enc.device)
+        check(_lib.lib().set_dcnet_caption_attention_forward(C.byref(dims), rows, P, C.byref(dae._struct), ptr(enc), ptr(h1),
+                                                             ptr(mask), ptr(scratch), n, ptr(out), _stream()))
+        return out
 
 
 class _DXEFunction(torch.autograd.Function):
@@ -85,6 +114,7 @@ class DAEBase(nn.Module):
 
     FIELDS = DCNET_FIELDS
     STRUCT = SetDcNetParams
+    LATE_FIELDS = ()
     # flat-parameter plumbing shared with EditNet
     _ordered_params = EditNetBase._ordered_params
     flatten_parameters = EditNetBase.flatten_parameters
@@ -100,14 +130,15 @@ class DAEBase(nn.Module):
             raise ValueError("the reference's concatenations require decoder_dim == emb_dim == "
                              "2 * caption_features_dim (dcnet.py:286-291)")
         self.vocab_size = len(word_map)
-        self.attention_lstm = nn.LSTMCell(emb_dim * 3, decoder_dim)
-        self.language_lstm = nn.LSTMCell(emb_dim * 2, decoder_dim)
+        self.attention_lstm = LSTMCellK(emb_dim * 3, decoder_dim)
+        self.language_lstm = LSTMCellK(emb_dim * 2, decoder_dim)
         self.embed = Embedding(word_map, emb_file, emb_dim, load_glove_embedding=False)
         self.caption_encoder = CaptionEncoder(len(word_map), emb_dim, caption_features_dim, caption_features_dim * 2,
                                               self.embed)
         self.caption_attention = CaptionAttention(caption_features_dim, decoder_dim, attention_dim)
-        self.fc = nn.Linear(decoder_dim, len(word_map))
+        self.fc = LinearK(decoder_dim, len(word_map))
         self.tanh = nn.Tanh()
+        self._link_submodules()
         self.decoder_dim = decoder_dim
         self.attention_dim = attention_dim
         self.dropout = nn.Dropout(0.5)
@@ -116,6 +147,14 @@ class DAEBase(nn.Module):
         self._struct = None
         self._last_call = None
         self.last_seed = None
+
+    def _link_submodules(self):
+        for m in (self.caption_encoder, self.caption_attention):
+            object.__setattr__(m, "_owner", weakref.ref(self))
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._link_submodules()
 
     def init_hidden_state(self, batch_size):
         dev = self.fc.weight.device

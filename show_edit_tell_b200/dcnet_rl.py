@@ -12,11 +12,15 @@ class DAE(DAEBase):
 
 
 class DAEWithAR(nn.Module):
-    """dcnet_rl.py:348-361.  The reference constructor `torch.load`s a checkpoint from a fixed path; here
-    the wrapped DAE is passed in (or built from a word map) so the class is usable without that file."""
+    """dcnet_rl.py:348-361.  `DAEWithAR()` does what the reference constructor does: `torch.load` the cross-entropy
+    checkpoint from `checkpoint` (the reference's fixed path by default) and wrap its 'dae' entry.  Alternatively the
+    wrapped DAE is passed in, or built from a word map, so the class is usable without that file."""
 
-    def __init__(self, dae=None, word_map=None, **kw):
+    def __init__(self, dae=None, word_map=None, checkpoint='BEST_checkpoint_3_dae.pth.tar', **kw):
         super().__init__()
+        if dae is None and word_map is None:
+            import torch
+            dae = torch.load(checkpoint, weights_only=False)['dae']          # dcnet_rl.py:355-356
         self.dae = dae if dae is not None else DAE(word_map, **kw)
         decoder_dim = self.dae.decoder_dim
         self.affine_hidden = nn.Linear(decoder_dim, decoder_dim)

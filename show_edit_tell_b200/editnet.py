@@ -10,6 +10,7 @@ without a CUDA device raises.
 """
 import ctypes as C
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -27,7 +28,67 @@ def _draw_seed():
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
-# --------------------------------------------------------------------- parameter shells
+# --------------------------------------------------------------------- sub-modules
+# The reference's beam searches call the decoder's sub-modules one by one (evaluate(), editnet.py:613,645-653;
+# eval/eval xe/eval_full.py:107-149), so each of them has a `forward` of its own: one library call computing exactly
+# what the reference module computes (nothing hoisted -- the caller owns the loop).  Inference surface: the results
+# carry no autograd graph; training goes through DecoderC.forward / the trainers.
+def _c(t):
+    return t.contiguous().float()
+
+
+class _Owned:
+    """sub-modules that need the decoder's whole parameter struct keep a weak reference to it"""
+
+    def _dec(self):
+        ref = getattr(self, "_owner", None)
+        dec = ref() if ref is not None else None
+        if dec is None:
+            raise RuntimeError("this sub-module is not attached to a decoder (construct it through DecoderC)")
+        dec._require_cuda(dec.fc.weight)
+        dec.flatten_parameters()
+        return dec
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_owner", None)
+        return state
+
+
+class LSTMCellK(nn.LSTMCell):
+    """nn.LSTMCell whose forward runs on the library's GEMM + cell kernels (attention_lstm, editnet.py:468,532)"""
+
+    def forward(self, input, hx=None):
+        if not input.is_cuda:
+            raise RuntimeError("show_edit_tell_b200 runs on a CUDA device only (no CPU fallback)")
+        rows = input.shape[0]
+        Dh = self.hidden_size
+        if hx is None:
+            z = torch.zeros(rows, Dh, device=input.device)
+            hx = (z, z)
+        x, h, c = _c(input), _c(hx[0]), _c(hx[1])
+        gates = torch.empty(rows, 4 * Dh, device=x.device)
+        h_out, c_out = torch.empty_like(h), torch.empty_like(c)
+        check(_lib.lib().set_lstm_cell_forward(rows, self.input_size, Dh, ptr(x), ptr(h), ptr(c), ptr(self.weight_ih),
+                                               ptr(self.weight_hh), ptr(self.bias_ih), ptr(self.bias_hh), ptr(gates),
+                                               ptr(h_out), ptr(c_out), _stream()))
+        return h_out, c_out
+
+
+class LinearK(nn.Linear):
+    """nn.Linear whose forward runs on the library's GEMM engine (fc, editnet.py:471,653)"""
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise RuntimeError("show_edit_tell_b200 runs on a CUDA device only (no CPU fallback)")
+        x = _c(input).view(-1, self.in_features)
+        out = torch.empty(x.shape[0], self.out_features, device=x.device)
+        check(_lib.lib().set_gemm(0, x.shape[0], self.out_features, self.in_features, ptr(x), self.in_features,
+                                  ptr(self.weight), self.in_features, ptr(self.bias), ptr(out), self.out_features, 0, 0,
+                                  _stream()))
+        return out.view(*input.shape[:-1], self.out_features)
+
+
 class LSTMCellC(nn.Module):
     """Parameter container of the encoder cell (editnet.py:210-244)."""
 
@@ -46,8 +107,8 @@ class LSTMCellC(nn.Module):
             p.data.uniform_(-std, std)
 
 
-class CopyLSTMCellC(nn.Module):
-    """Parameter container of the copy-LSTM (editnet.py:247-285)."""
+class CopyLSTMCellC(_Owned, nn.Module):
+    """The copy-LSTM (editnet.py:247-285); forward(x, (h, c), c_mem) -> (h, c) as :265-285."""
 
     def __init__(self, input_size, hidden_size):
         super().__init__()
@@ -65,6 +126,18 @@ class CopyLSTMCellC(nn.Module):
         for p in self.parameters():
             p.data.uniform_(-std, std)
 
+    def forward(self, x, states, c_mem):
+        dec = self._dec()
+        rows = x.shape[0]
+        x, h, c, mem = _c(x), _c(states[0]), _c(states[1]), _c(c_mem)
+        dims = dec._dims()
+        n = _lib.lib().set_copy_lstm_scratch_floats(C.byref(dims), rows)
+        scratch = torch.empty(n, device=x.device)
+        h_out, c_out = torch.empty_like(h), torch.empty_like(c)
+        check(_lib.lib().set_copy_lstm_forward(C.byref(dims), rows, C.byref(dec._struct), ptr(x), ptr(h), ptr(c), ptr(mem),
+                                               ptr(scratch), n, ptr(h_out), ptr(c_out), _stream()))
+        return h_out, c_out
+
 
 class EmbeddingC(nn.Module):
     """editnet.py:288-304"""
@@ -77,9 +150,21 @@ class EmbeddingC(nn.Module):
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(0.5)
 
+    def forward(self, x):
+        """dropout(relu(Emb[x])), editnet.py:300-304; x int64 of any shape -> x.shape + (emb_dim,)"""
+        if not x.is_cuda:
+            raise RuntimeError("show_edit_tell_b200 runs on a CUDA device only (no CPU fallback)")
+        tok = x.contiguous().view(-1)
+        table = self.embedding.weight
+        out = torch.empty(tok.numel(), self.emb_dim, device=x.device)
+        seed = _draw_seed() if self.training else 0
+        check(_lib.lib().set_embed_forward(ptr(tok), tok.numel(), ptr(table), table.shape[0], self.emb_dim,
+                                           int(self.training), seed, ptr(out), _stream()))
+        return out.view(*x.shape, self.emb_dim)
 
-class CaptionEncoderC(nn.Module):
-    """editnet.py:307-348"""
+
+class CaptionEncoderC(_Owned, nn.Module):
+    """editnet.py:307-348; forward(seq, seq_len) -> (hidden_states, memory_states, final_hidden, mask) as :319-348"""
 
     def __init__(self, vocab_size, emb_dim, enc_hid_dim, embed):
         super().__init__()
@@ -91,9 +176,12 @@ class CaptionEncoderC(nn.Module):
         self.affine_hn = nn.Linear(enc_hid_dim, enc_hid_dim)
         self.tanh = nn.Tanh()
 
+    def forward(self, seq, seq_len):
+        return self._dec().encode(seq, seq_len)
 
-class CaptionAttentionC(nn.Module):
-    """editnet.py:351-381"""
+
+class CaptionAttentionC(_Owned, nn.Module):
+    """editnet.py:351-381; forward(prev_h, h1, word, mask) -> (gated context, alpha) as :364-381"""
 
     def __init__(self, caption_features_dim, decoder_dim, attention_dim):
         super().__init__()
@@ -105,16 +193,40 @@ class CaptionAttentionC(nn.Module):
         self.tc_affine = nn.Linear(decoder_dim * 2, caption_features_dim)
         self.tanh = nn.Tanh()
 
+    def forward(self, prev_cap_features, decoder_hidden, word, prev_cap_mask):
+        dec = self._dec()
+        prev_h, h1, emb, mask = _c(prev_cap_features), _c(decoder_hidden), _c(word), _c(prev_cap_mask)
+        rows, P = prev_h.shape[0], prev_h.shape[1]
+        dims = dec._dims()
+        n = _lib.lib().set_caption_attention_scratch_floats(C.byref(dims), rows, P)
+        scratch = torch.empty(n, device=prev_h.device)
+        out = torch.empty(rows, dec.decoder_dim, device=prev_h.device)
+        alpha = torch.empty(rows, P, device=prev_h.device)
+        check(_lib.lib().set_caption_attention_forward(C.byref(dims), rows, P, C.byref(dec._struct), ptr(prev_h), ptr(h1),
+                                                       ptr(emb), ptr(mask), ptr(scratch), n, ptr(out), ptr(alpha),
+                                                       _stream()))
+        return out, alpha
+
 
 class SelectC(nn.Module):
-    """editnet.py:383-421 (no parameters)"""
+    """editnet.py:383-421 (no parameters); forward(prev_m, alpha) -> selected memory row as :403-421"""
 
     def __init__(self, prev_caption_dim, decoder_dim):
         super().__init__()
 
+    def forward(self, previous_encoded_m, alpha_c):
+        if not previous_encoded_m.is_cuda:
+            raise RuntimeError("show_edit_tell_b200 runs on a CUDA device only (no CPU fallback)")
+        m, a = _c(previous_encoded_m), _c(alpha_c)
+        rows, P, Dm = m.shape
+        out = torch.empty(rows, Dm, device=m.device)
+        check(_lib.lib().set_select_forward(rows, P, Dm, ptr(m), ptr(a), ptr(out), _stream()))
+        return out
 
-class VisualAttentionC(nn.Module):
-    """editnet.py:424-447"""
+
+class VisualAttentionC(_Owned, nn.Module):
+    """editnet.py:424-447 (adaptive_features/editnet_adaptive.py:423-457 when the decoder is the adaptive variant);
+    forward(image_features, decoder_hidden) -> attended features as :439-447"""
 
     def __init__(self, image_features_dim, decoder_dim, attention_dim):
         super().__init__()
@@ -123,6 +235,20 @@ class VisualAttentionC(nn.Module):
         self.decoder_att = nn.Linear(decoder_dim, attention_dim)
         self.full_att = nn.Linear(attention_dim, 1)
         self.softmax = nn.Softmax(dim=1)
+
+    def forward(self, image_features, decoder_hidden):
+        dec = self._dec()
+        feats, h1 = _c(image_features), _c(decoder_hidden)
+        rows, R = feats.shape[0], feats.shape[1]
+        dims = dec._dims()
+        n = _lib.lib().set_visual_attention_scratch_floats(C.byref(dims), rows, R)
+        scratch = torch.empty(n, device=feats.device)
+        out = torch.empty(rows, dec.image_features_dim, device=feats.device)
+        seed = _draw_seed() if self.training else 0
+        check(_lib.lib().set_visual_attention_forward(C.byref(dims), rows, R, C.byref(dec._struct), ptr(feats), ptr(h1),
+                                                      int(dec.ADAPTIVE), int(self.training), seed, ptr(scratch), n,
+                                                      ptr(out), _stream()))
+        return out
 
 
 # ------------------------------------------------------------------------- autograd edge
@@ -185,15 +311,20 @@ class EditNetBase(nn.Module):
         self.caption_attention = CaptionAttentionC(caption_features_dim, decoder_dim, attention_dim)
         self.visual_attention = VisualAttentionC(image_features_dim, decoder_dim, attention_dim)
         self.select = SelectC(caption_features_dim, decoder_dim)
-        self.attention_lstm = nn.LSTMCell((emb_dim * 3) + image_features_dim, decoder_dim)
+        self.attention_lstm = LSTMCellK((emb_dim * 3) + image_features_dim, decoder_dim)
         self.copy_lstm = CopyLSTMCellC((emb_dim * 2) + image_features_dim, decoder_dim)
         self.tanh = nn.Tanh()
-        self.fc = nn.Linear(decoder_dim, self.vocab_size)
+        self.fc = LinearK(decoder_dim, self.vocab_size)
+        self._link_submodules()
         self._flat = None
         self._offsets = None
         self._struct = None
         self._last_call = None
         self.last_seed = None
+
+    def _link_submodules(self):
+        for m in (self.caption_encoder, self.caption_attention, self.visual_attention, self.copy_lstm):
+            object.__setattr__(m, "_owner", weakref.ref(self))
 
     def __getstate__(self):
         # ctypes structs / cached calls are rebuilt lazily; parameters are pickled as ordinary tensors
@@ -202,6 +333,10 @@ class EditNetBase(nn.Module):
             state[k] = None
         return state
 
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._link_submodules()
+
     def init_hidden_state(self, batch_size):
         dev = self.fc.weight.device
         return (torch.zeros(batch_size, self.decoder_dim, device=dev),
@@ -209,6 +344,8 @@ class EditNetBase(nn.Module):
 
     FIELDS = EDITNET_FIELDS
     STRUCT = SetEditNetParams
+    LATE_FIELDS = ("embed", "enc_x2h_w", "enc_x2h_b", "enc_h2h_w", "enc_h2h_b", "enc_aff_w", "enc_aff_b",
+                   "va_emb_w", "va_emb_b", "va_feat_w", "va_feat_b")
 
     # ---- flat parameter storage: every parameter is a view into one buffer, so the optimizer
     # tail and the data-parallel all-reduce see a single tensor
@@ -222,10 +359,17 @@ class EditNetBase(nn.Module):
             base = self._flat.data_ptr()
             if all(p.data_ptr() == base + 4 * o for p, o in zip(params, self._offsets)):
                 return self._flat
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
-            total += (p.numel() + 63) // 64 * 64
+        # Layout of the flat buffer: the parameters whose gradients are final LAST in the reverse pass (embedding table,
+        # caption encoder, att_embed / features_att: LATE_FIELDS) come first, everything else behind them -- the early-
+        # final "tail" is then one contiguous range that a data-parallel step all-reduces underneath the rest of the
+        # reverse pass (train.py, set_backward_bucket_notify).
+        names = [n for n, _ in self.FIELDS]
+        order = [names.index(n) for n in self.LATE_FIELDS] + [i for i, n in enumerate(names) if n not in self.LATE_FIELDS]
+        offs, total = [0] * len(params), 0
+        for i in order:
+            offs[i] = total
+            total += (params[i].numel() + 63) // 64 * 64
+        self._tail_offset = offs[order[len(self.LATE_FIELDS)]] if len(self.LATE_FIELDS) < len(params) else total
         flat = torch.zeros(total, device=dev, dtype=torch.float32)
         for p, o in zip(params, offs):
             view = flat[o:o + p.numel()].view(p.shape)

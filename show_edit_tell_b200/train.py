@@ -39,9 +39,9 @@ class XETrainer:
         self.gpu_launches_last_step = 0
 
     def _tail_offset(self):
-        """first element of the gradient tail that is final early in the reverse pass (attention_lstm.weight_ih on)"""
-        names = [n for n, _ in self.decoder.FIELDS]
-        return self.decoder._offsets[names.index("al_wih")]
+        """first element of the gradient range that is final early in the reverse pass: everything behind the embedding
+        table, the caption encoder and att_embed / features_att in the flat layout (EditNetBase.flatten_parameters)"""
+        return self.decoder._tail_offset
 
     def _allreduce_overlapped(self, grad, n, local_count, run_backward):
         """run_backward() enqueues the reverse pass; the tail bucket (+ the count slot behind it) is all-reduced on a
