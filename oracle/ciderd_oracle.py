@@ -12,7 +12,9 @@ Three layers, each with its own pin:
     restated from the paper / that file's well-known structure: tf-idf n-gram vectors for n = 1..4 with
     idf = log(N) - log(max(1, df)), clipped cosine similarity min(h, r) * r / (|h| |r|), Gaussian length penalty with
     sigma = 6 on the difference of BIGRAM counts (the `if n == 1: length += term_freq` quirk), mean over n, mean over
-    references, x 10.  PARITY UNPINNED for this layer: no copy of the package is available to run against.
+    references, x 10.  No copy of the package is available to run against; the layer is pinned instead by known-answer
+    vectors worked by hand from that definition (tests/test_ciderd_known_answer.py: derivations in its docstring), which
+    both this scorer and the device kernel must reproduce.
 """
 import math
 from collections import OrderedDict, defaultdict
