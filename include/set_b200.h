@@ -330,6 +330,26 @@ SET_API int set_copy_lstm_forward(const SetDims* dims, int rows, const SetEditNe
                                   const float* h, const float* c, const float* mem, float* scratch,
                                   size_t scratch_floats, float* h_out, float* c_out, void* stream);
 
+/* ---- Batched beam search on the device: the expansion step of evaluate(), editnet.py:654-696,
+ * and of the ensemble evaluate_full(), eval/eval xe/eval_full.py:151-191, for N images x K beams at once (rows
+ * image * K + beam of one step session).  Per image: log-softmax of the live beams' scores (logits_d != NULL:
+ * log((softmax_e + softmax_d) / 2)), cumulative add, top-k over (live beams x V) -- beam 0 only at step 1 -- sequence
+ * extension, <end> bookkeeping (completed beams move to the completion store, k_live shrinks), next input tokens and
+ * the rows the state re-gather reads (src_row).  live_images counts images that still have live beams. */
+SET_API int set_beam_expand(int N, int K, int V, int step, int Lmax, int64_t end_tok, const float* logits_e,
+                            const float* logits_d, int* k_live, float* beam_scores, const int64_t* seq_in, int64_t* seq_out,
+                            int64_t* next_tokens, int* src_row, int* n_complete, float* complete_scores,
+                            int64_t* complete_seqs, int* complete_len, int* live_images, void* stream);
+/* out_s[r] = in_s[src_row[r]] for the four state tensors (rows x D) */
+SET_API int set_beam_gather(int rows, int D, const int* src_row, const float* in0, const float* in1, const float* in2,
+                            const float* in3, float* out0, float* out1, float* out2, float* out3, void* stream);
+/* per image: the completed beam with the highest score (first occurrence), or -- runaway guard, editnet.py:702-713 --
+ * the first 18 tokens of the first live beam */
+SET_API int set_beam_finalize(int N, int K, int Lmax, int steps_done, const int* k_live, const int64_t* seq_live,
+                              const float* beam_scores, const int* n_complete, const float* complete_scores,
+                              const int64_t* complete_seqs, const int* complete_len, int64_t* out_seq, int* out_len,
+                              float* out_score, void* stream);
+
 /* Data-parallel overlap (new: the reference is single-process).  Arms the NEXT set_editnet_xe_backward /
  * set_editnet_rollout_backward call of this thread: when every parameter gradient except those of embed.*,
  * caption_encoder.* and visual_attention.att_embed / features_att is final (about two thirds into the reverse pass:

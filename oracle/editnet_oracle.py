@@ -352,6 +352,7 @@ def beam_search(sd, word_map, feats, prev, prev_len, beam_size=3, max_steps=50):
     done_seqs, done_scores = [], []
     st = tuple(feats.new_zeros(k, D) for _ in range(4))
     step = 1
+    runaway = False
     while True:
         n = words.shape[0]
         e = embed(sd, words)
@@ -376,10 +377,11 @@ def beam_search(sd, word_map, feats, prev, prev_len, beam_size=3, max_steps=50):
         st = tuple(x[pi[inc]] for x in st)
         top = top_s[inc].unsqueeze(1)
         words = ni[inc]
-        if step > max_steps:
+        if step > max_steps:                                                                # :702
+            runaway = True
             break
         step += 1
-    if not done_scores:
-        return seqs[0].tolist(), float(top[0])
+    if runaway or not done_scores:
+        return seqs[0][:18].tolist(), float(top[0])                                         # :710-711
     i = done_scores.index(max(done_scores))
     return done_seqs[i], done_scores[i]

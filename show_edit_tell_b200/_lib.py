@@ -180,6 +180,10 @@ _SIGS = {
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm_twin_launches": (C.c_longlong, [C.c_int]),
     "set_backward_bucket_notify": (C.c_int, [_P]),
+    "set_beam_expand": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P, _P, _P, _P, _P]),
+    "set_beam_gather": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "set_beam_finalize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "set_embed_forward": (C.c_int, [_P, C.c_long, _P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "set_lstm_cell_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "set_caption_attention_scratch_floats": (C.c_size_t, [C.POINTER(SetDims), C.c_int, C.c_int]),

@@ -287,6 +287,12 @@ class DStepSession:
                                         ptr(scores), ptr(self.ws), self.ws.numel(), _stream()))
         return scores, tuple(st)
 
+    def step_raw(self, tokens, state, scores):
+        """in place: `state` = [h1, c1, h2, c2] (B, D) buffers are advanced, `scores` (B, V) receives fc(h2)"""
+        check(_lib.lib().set_dcnet_step(C.byref(self.dims), C.byref(self.shape), C.byref(self.mod._struct), ptr(tokens),
+                                        self.shape.B, ptr(state[0]), ptr(state[1]), ptr(state[2]), ptr(state[3]),
+                                        ptr(scores), ptr(self.ws), self.ws.numel(), _stream()))
+
 
 def _dstep_session(self, encoded_previous_captions, previous_cap_length):
     return DStepSession(self, encoded_previous_captions, previous_cap_length)

@@ -615,6 +615,12 @@ class StepSession:
                                           ptr(st[2]), ptr(st[3]), ptr(scores), ptr(self.ws), self.ws.numel(), _stream()))
         return scores, tuple(st)
 
+    def step_raw(self, tokens, state, scores):
+        """in place: `state` = [h1, c1, h2, c2] (B, D) buffers are advanced, `scores` (B, V) receives fc(h2)"""
+        check(_lib.lib().set_editnet_step(C.byref(self.dims), C.byref(self.shape), C.byref(self.mod._struct),
+                                          ptr(self.feats), ptr(tokens), self.shape.B, ptr(state[0]), ptr(state[1]),
+                                          ptr(state[2]), ptr(state[3]), ptr(scores), ptr(self.ws), self.ws.numel(), _stream()))
+
 
 def _step_session(self, image_features, encoded_previous_captions, previous_cap_length, image_mean=None):
     return StepSession(self, image_features, encoded_previous_captions, previous_cap_length, image_mean)
