@@ -54,6 +54,9 @@ WORKLOADS = {
     "adaptive": dict(config=4, metric="captions/sec (EditNet adaptive XE train, ragged 10-100 regions, B=64)",
                      text="EditNet adaptive XE train step (editnet_adaptive.py:489-562), ragged 10..100 region features "
                           "zero-padded to 100, B=64/GPU, seq_len=20 (T=19), V=10000, dropout on"),
+    "beam64": dict(config=2, metric="captions/sec (EditNet beam-3 search, 64 images per call)",
+                   text="EditNet beam search (evaluate(), editnet.py:595-719: beam 3, the reference's eval path) batched over "
+                        "64 images x 3 beams in one step session with device-side expansion (beam.py), 36x2048 feats, V=10000"),
     "dcnet4": dict(config=0, metric="captions/sec (DCNet XE teacher-forced forward, B=4)",
                    text="DCNet XE teacher-forced forward (dcnet.py:303-350), B=4, seq_len=20 (T=19), V=10000, eval mode"),
 }
@@ -174,6 +177,15 @@ def cpu_step_fn(workload, rows):
             with torch.no_grad():
                 EO.rollout(sd, b["prev"], b["prev_len"], b["feats"], V - 2, V - 1, "greedy")
         return step, rows, "greedy rollout, eval mode"
+    if workload == "beam64":
+        wm = osynth.word_map(V)
+
+        def step():
+            with torch.no_grad():
+                for i in range(rows):     # the reference searches one image at a time (batch-1 loader, editnet.py:795-798)
+                    EO.beam_search(sd, wm, b["feats"][i:i + 1], b["prev"][i:i + 1], b["prev_len"][i:i + 1], beam_size=3,
+                                   max_steps=20)
+        return step, rows, "per-image beam-3 search, eval mode, capped at 21 steps like the b200 arm"
     if workload == "scst":
         forced = torch.randint(1, V - 4, (rows, 18))
         reward = torch.randn(rows, 1).repeat(1, 18)
@@ -201,7 +213,7 @@ def time_cpu(workload, rows, n_timed, n_warm):
     return caps / dt, dt, desc
 
 
-CPU_ROWS = {"xe": 64, "adaptive": 64, "greedy256": 256, "scst": 64, "dcnet4": 4}
+CPU_ROWS = {"xe": 64, "adaptive": 64, "greedy256": 256, "scst": 64, "dcnet4": 4, "beam64": 8}
 
 
 def run_reference(args, rank, world):
@@ -320,6 +332,20 @@ def main():
             return seq
         steps_per_call, alg_bytes = 18, W_REC_AR + 256 * s_bytes(R, True)
         roof_kernel = "autoregressive decode step (launch chain: embedding, word projections, step GEMMs + cells, attention, fc, sampler)"
+    elif wl == "beam64":
+        from show_edit_tell_b200.beam import beam_search_batched
+        dec = editnet.DecoderC(wm, D, D, D, A, FD).to(dev).eval()
+        host = synth.make_batch(64, V, R, FD, CAPW, PREVW, seed=11 + rank, pinned=True)
+        keys = ("feats", "prev", "prev_len")
+        rows_per_step = 64
+
+        def run(batch, hostb=None):
+            # a random-init model never emits <end>: the search is capped at 21 steps (the oracle arm uses the same cap)
+            with torch.no_grad():
+                res = beam_search_batched(dec, wm, batch[0], batch[1], batch[2], beam_size=3, max_steps=20)
+            return torch.tensor([len(r[0]) for r in res], dtype=torch.int64)
+        steps_per_call, alg_bytes = 21, W_REC_AR + 192 * s_bytes(R, True)
+        roof_kernel = "autoregressive decode step on 64 x 3 beam rows (launch chain + fc + beam expansion kernel + state re-gather)"
     elif wl == "scst":
         dec = editnet_rl.DecoderC(wm, D, D, D, A, FD).to(dev)
         trainer = SCSTTrainer(dec, distributed=(world > 1))
