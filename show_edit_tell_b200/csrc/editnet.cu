@@ -541,13 +541,18 @@ int steps_persistent(Ctx& c, const float* feats, int t0, int nt, const int* bt, 
     seg(*p, D, mGcm, 0, mQsel, 0, 0); p->nblk = 1; p->N = D; p->bias = w.cl_gcm_b; p->bias2 = w.cl_gcn_b;
     p->C = TP(s.s4 + 2 * D, 3 * BD); p->ldc = 3 * D;
     ph.prob[ph.nprob++] = np++;
+    // x2h[:, 2D:] att_img: the first half of its K range here, the second half rides with phase E (whose own K is
+    // short), so that no CTA of this phase carries more than ~16 K-blocks
+    const int Fh = (F / 2) / 32 * 32;
     p = &prm.prob[np];
-    seg(*p, F, mX2h128, 2 * D, mQX2, 2 * D, 0); p->nblk = 1; p->N = 4 * D; p->C = TP(s.g2, 4 * BD); p->ldc = 4 * D; p->beta = 1;
+    seg(*p, Fh, mX2h128, 2 * D, mQX2, 2 * D, 0); p->nblk = 1; p->N = 4 * D; p->C = TP(s.g2, 4 * BD); p->ldc = 4 * D; p->beta = 1;
     ph.prob[ph.nprob++] = np++;
   }
-  {  // phase E: x2h[:, D:2D] att_cap + copy-LSTM stage 1
+  {  // phase E: x2h[:, D:2D] att_cap (+ the second half of x2h[:, 2D:] att_img) + copy-LSTM stage 1
+    const int Fh = (F / 2) / 32 * 32;
     StepProb& p = prm.prob[np];
     seg(p, D, mX2h32, D, mQX2, D, 0);
+    seg(p, F - Fh, mX2h32, 2 * D + Fh, mQX2, 2 * D + Fh, 0);
     p.nblk = 4; p.blk_stride = D; p.N = D; p.epi = kSEpiCopy1; p.beta = 1;
     p.C = TP(s.g2, 4 * BD); p.ldc = 4 * D;
     p.a0 = TP(s.c2, BD); p.a1 = TP(s.cnew, BD);

@@ -46,10 +46,11 @@ namespace set {
 namespace {
 
 #ifndef SET_STEP_NP
-#define SET_STEP_NP 6
+#define SET_STEP_NP 4
 #endif
 constexpr int kNP = SET_STEP_NP;       // weight ring slots (16 KB each): what keeps HBM requests in flight
-constexpr int kNQ = 6;                 // activation (Q) slots: raw | lo, 16 KB each
+constexpr int kNQ = 12;                // raw activation (Q) tiles in flight, 8 KB each: a job's Q operand lands in one round trip
+constexpr int kNL = 4;                 // lo tiles (x - hi), 8 KB each, recycled at the MMA's pace
 constexpr int kNT = 7;                 // tensor-memory slots of converted weight tiles (hi | lo, 64 columns each)
 constexpr int kQN = 64;                // batch rows of the Q tile
 constexpr int kTileP = 128;
@@ -57,12 +58,12 @@ constexpr int kBlockK = 32;
 constexpr int kThreads = 512;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kFirstConvWarp = 4;      // warps 4..7: weight converters
+constexpr int kFirstConvWarp = 4;      // warps 4..7: weight converters (one warp per tensor-memory lane quarter)
+constexpr int kConvGroups = 1;         // (two groups alternating K-blocks -- 608 threads, 96 registers -- measured slower: 114 vs 94 us per step)
 constexpr int kFirstEpiWarp = 8;       // warps 8..15: Q lo-split, epilogue / finish, attention, grid barriers
 constexpr int kMaxSplit = 4;            // split-K partners are the CTAs of one thread-block cluster
 constexpr int kPBytes = kTileP * 128;  // 16 KB
 constexpr int kQBytes = kQN * 128;     // 8 KB
-constexpr int kQSlot = 2 * kQBytes;    // raw (= hi) | lo
 constexpr int kAttnCols = 256;         // columns of a staged value chunk
 constexpr int kAttnRows = 36;          // rows of a staged value chunk (box rows <= this)
 constexpr int kAttnBuf = kAttnRows * kAttnCols * 4;
@@ -72,10 +73,10 @@ constexpr int kAttnMaxN = 128;         // max(P, R) supported by the persistent 
 constexpr int kAttnMaxItems = 32;      // (sample, column slice) items of one CTA in phase C2
 constexpr int kAttnMaxUnits = 96;      // value chunks of one CTA in phase C2
 constexpr int kEpPitch = kTileP + 4;   // staged accumulator tile: [64 q][128 p], padded
-constexpr int kStageBytes = kAttnBufs * kAttnBuf;            // 110592: aliases Q ring (64 KB) / accumulator tile (33 KB)
-static_assert(kStageBytes >= kNQ * kQSlot && kStageBytes >= kQN * kEpPitch * 4, "staging region too small");
+constexpr int kStageBytes = (kNQ + kNL) * kQBytes;           // 131072: Q raw + lo rings; aliased by the accumulator tile (33 KB)
+static_assert(kStageBytes >= kAttnBufs * kAttnBuf && kStageBytes >= kQN * kEpPitch * 4, "staging region too small");  // and the attention chunks
 static_assert(64 + 64 * kNT <= 512, "tensor memory: accumulator + converted weight slots");
-constexpr int kNumBars = 2 * kNP + 2 * kNT + 3 * kNQ + 1 + kAttnBufs + kMaxSplit;
+constexpr int kNumBars = 2 * kNP + 2 * kNT + 2 * kNQ + 2 * kNL + 1 + kAttnBufs + kMaxSplit;
 constexpr int kSmallBytes = 8 * kNumBars + 16 /*tmem slot, flags*/ + 4 * (kAttnBatch * kAttnMaxN + 4 * kAttnBatch) + 256 /*jobs*/ + 16 * (kAttnMaxUnits + kAttnMaxItems);
 constexpr int kSmemBytes = 1024 + kNP * kPBytes + kStageBytes + ((kSmallBytes + 127) & ~127);
 constexpr uint32_t kTmemCols = 512;
@@ -87,7 +88,7 @@ constexpr uint32_t kTmemCols = 512;
 #ifdef SET_STEP_FINE_TRACE
 #define FS(s_, ph_, k_)                                                                                   \
   do {                                                                                                    \
-    if (P.trace && blockIdx.x == 0) P.trace[(long)P.nt * 8 * gridDim.x + ((s_) * 5 + (ph_)) * 16 + (k_)] = gtimer(); \
+    if (P.trace && (int)blockIdx.x == P.trace_cta) P.trace[(long)P.nt * 8 * gridDim.x + ((s_) * 5 + (ph_)) * 16 + (k_)] = gtimer(); \
   } while (0)
 #else
 #define FS(s_, ph_, k_) do { } while (0)
@@ -159,12 +160,14 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
   auto p_empty = [&](int s) { return bar_base + 8u * (kNP + s); };                         // weight tile converted
   auto pconv_bar = [&](int s) { return bar_base + 8u * (2 * kNP + s); };                   // hi | lo in tensor memory
   auto t_empty = [&](int s) { return bar_base + 8u * (2 * kNP + kNT + s); };               // tensor-memory slot consumed
-  auto q_full = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + s); };            // activation tile landed
-  auto qconv_bar = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + kNQ + s); };   // its lo part written
-  auto q_empty = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + 2 * kNQ + s); }; // activation slot consumed
-  const uint32_t accum_bar = bar_base + 8u * (2 * kNP + 2 * kNT + 3 * kNQ);
-  auto attn_full = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + 3 * kNQ + 1 + s); };
-  auto xch_bar = [&](int r) { return bar_base + 8u * (2 * kNP + 2 * kNT + 3 * kNQ + 1 + kAttnBufs + r); };   // "partial tile of cluster rank r is staged"
+  auto q_full = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + s); };                   // raw activation tile landed
+  auto q_empty = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + kNQ + s); };            // raw tile consumed
+  auto qconv_bar = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + 2 * kNQ + s); };      // lo tile written
+  auto l_empty = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + 2 * kNQ + kNL + s); };  // lo tile consumed
+  const uint32_t accum_bar = bar_base + 8u * (2 * kNP + 2 * kNT + 2 * kNQ + 2 * kNL);
+  auto attn_full = [&](int s) { return bar_base + 8u * (2 * kNP + 2 * kNT + 2 * kNQ + 2 * kNL + 1 + s); };
+  auto xch_bar = [&](int r) { return bar_base + 8u * (2 * kNP + 2 * kNT + 2 * kNQ + 2 * kNL + 1 + kAttnBufs + r); };   // "partial tile of cluster rank r is staged"
+  const uint32_t lo_base = stage + kNQ * kQBytes;        // lo ring behind the raw ring
   const uint32_t tmem_slot = bar_base + 8u * kNumBars;
   float* alpha_s = reinterpret_cast<float*>(gen_small + 8 * kNumBars + 16);      // [kAttnBatch][kAttnMaxN]
   int* js_s = reinterpret_cast<int*>(alpha_s + kAttnBatch * kAttnMaxN);            // [kAttnBatch] argmax
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNP; ++s) { mbar_init(p_full(s), 1); mbar_init(p_empty(s), 4); }
     for (int s = 0; s < kNT; ++s) { mbar_init(pconv_bar(s), 4); mbar_init(t_empty(s), 1); }
-    for (int s = 0; s < kNQ; ++s) { mbar_init(q_full(s), 1); mbar_init(qconv_bar(s), kEpiWarps); mbar_init(q_empty(s), 1); }
+    for (int s = 0; s < kNQ; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+    for (int s = 0; s < kNL; ++s) { mbar_init(qconv_bar(s), kEpiWarps); mbar_init(l_empty(s), 1); }
     mbar_init(accum_bar, 1);
     for (int s = 0; s < kAttnBufs; ++s) mbar_init(attn_full(s), 1);
     for (int r = 0; r < kMaxSplit; ++r) mbar_init(xch_bar(r), 1);
@@ -230,17 +234,17 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kQN >> 3) << 17) | ((uint32_t)(kTileP >> 4) << 24);
-    RingPos rt, rq;
+    RingPos rt, rq, rl;
     for (int s = 0; s < P.nt; ++s) {
       for (int ph = 0; ph < kStepGemmPhases; ++ph) {
         const Job j = jobs[ph];
         if (j.prob < 0) continue;
         for (int kb = j.kb_begin; kb < j.kb_end; ++kb) {
           mbar_wait_guarded(pconv_bar(rt.slot), rt.phase);
-          mbar_wait_guarded(qconv_bar(rq.slot), rq.phase);
+          mbar_wait_guarded(qconv_bar(rl.slot), rl.phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            const uint32_t q_hi = stage + rq.slot * kQSlot, q_lo = q_hi + kQBytes;
+            const uint32_t q_hi = stage + rq.slot * kQBytes, q_lo = lo_base + rl.slot * kQBytes;
             const uint64_t b_hi0 = umma_desc(q_hi, 16u, 1024u), b_lo0 = umma_desc(q_lo, 16u, 1024u);
             const uint32_t ta0 = tmem_base + (uint32_t)kQN + rt.slot * 64u;
 #pragma unroll
@@ -253,10 +257,11 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
             }
             umma_commit(t_empty(rt.slot));
             umma_commit(q_empty(rq.slot));
+            umma_commit(l_empty(rl.slot));
             if (kb == j.kb_end - 1) umma_commit(accum_bar);
           }
           __syncwarp();
-          rt.advance(kNT); rq.advance(kNQ);
+          rt.advance(kNT); rq.advance(kNQ); rl.advance(kNL);
         }
       }
     }
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
           if (rq.wrapped) mbar_wait_guarded(q_empty(rq.slot), rq.phase ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(q_full(rq.slot), kQBytes);
-            tma_load_3d(stage + rq.slot * kQSlot, &P.maps[pr.qmap[sg]], q_full(rq.slot), pr.qcol0[sg] + kk * kBlockK, 0, t + pr.qtoff[sg]);
+            tma_load_3d(stage + rq.slot * kQBytes, &P.maps[pr.qmap[sg]], q_full(rq.slot), pr.qcol0[sg] + kk * kBlockK, 0, t + pr.qtoff[sg]);
           }
           __syncwarp();
           rq.advance(kNQ);
@@ -297,13 +302,20 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
     // A landed fp32 weight tile goes to tensor memory as hi | lo (the MMA's A operand) as soon as a slot is free --
     // independent of the activations, so the tiles of the NEXT phase are converted while this phase still drains,
     // reduces and synchronises: up to kNT converted + kNP landed tiles wait on chip when a phase opens.
+    // Two groups alternate K-blocks.  A group therefore sees only every other use of a slot; that is safe because each
+    // wait names the exact use (parity from the global K-block position) and no barrier can run two phases ahead of its
+    // waiter: the next load of a weight slot needs this conversion's p_empty arrival, the next MMA on a tensor-memory
+    // slot needs this conversion's pconv arrival.
     const int quarter = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - kFirstConvWarp) >> 2;
     RingPos rp, rt;
+    uint32_t seq = 0;
     for (int s = 0; s < P.nt; ++s) {
       for (int ph = 0; ph < kStepGemmPhases; ++ph) {
         const Job j = jobs[ph];
         if (j.prob < 0) continue;
-        for (int kb = j.kb_begin; kb < j.kb_end; ++kb) {
+        for (int kb = j.kb_begin; kb < j.kb_end; ++kb, ++seq) {
+          if ((seq & (kConvGroups - 1)) != grp) { rp.advance(kNP); rt.advance(kNT); continue; }
           if (rt.wrapped) mbar_wait_guarded(t_empty(rt.slot), rt.phase ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           mbar_wait_guarded(p_full(rp.slot), rp.phase);
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
     const int ew = warp - kFirstEpiWarp;               // 0 .. 7
     const int quarter = warp & 3;                      // tensor-memory lane quarter of this warp
     float* ep = reinterpret_cast<float*>(gen_stage);
-    RingPos rq;
+    RingPos rq, rl;
     uint32_t jobseq = 0, barseq = 0;
     uint32_t xph = 0;                            // bit r: parity of the next completion of xch_bar(r)
     uint32_t attn_units_done = 0;                // value chunks consumed since launch (ring slot / parity)
@@ -413,8 +425,9 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
               mbar_wait_guarded(q_full(rq.slot), rq.phase);
               if (i == 0 && ct == 0) FS(s, ph, 1);
               if (i == nkb - 1 && ct == 0) FS(s, ph, 3);
-              float4* q_hi = reinterpret_cast<float4*>(gen_stage + rq.slot * kQSlot);
-              float4* q_lo = reinterpret_cast<float4*>(gen_stage + rq.slot * kQSlot + kQBytes);
+              if (rl.wrapped) mbar_wait_guarded(l_empty(rl.slot), rl.phase ^ 1u);
+              const float4* q_hi = reinterpret_cast<const float4*>(gen_stage + rq.slot * kQBytes);
+              float4* q_lo = reinterpret_cast<float4*>(gen_stage + (kNQ + rl.slot) * kQBytes);
 #pragma unroll
               for (int jj = 0; jj < kQBytes / 16 / kEpiThreads; ++jj) {
                 const float4 v = q_hi[ct + kEpiThreads * jj];
@@ -427,8 +440,8 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const __grid_constant
               }
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
               __syncwarp();
-              if (lane == 0) mbar_arrive(qconv_bar(rq.slot));
-              rq.advance(kNQ);
+              if (lane == 0) mbar_arrive(qconv_bar(rl.slot));
+              rq.advance(kNQ); rl.advance(kNL);
             }
             // ---- accumulator -> registers -> shared (staged as [q][p]; the Q ring is idle now)
             mbar_wait_guarded(accum_bar, jobseq & 1u);
@@ -928,6 +941,7 @@ int step_launch(StepParams& prm, int grid, int cluster, cudaStream_t stream) {
   if (!prm.sync) return SET_ERR_CUDA;
   prm.slabs = nullptr;
   prm.trace = g_step_trace;
+  prm.trace_cta = getenv("SET_STEP_TRACE_CTA") ? atoi(getenv("SET_STEP_TRACE_CTA")) : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;

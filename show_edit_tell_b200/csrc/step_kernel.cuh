@@ -84,6 +84,7 @@ struct StepParams {
   int train; unsigned long long seed;
   unsigned int* sync;               // [0] grid barrier, [1] exit counter
   float* slabs;                     // (unused: split-K partials meet in distributed shared memory)
+  int trace_cta;                    // CTA whose fine-grained stamps are recorded (-DSET_STEP_FINE_TRACE builds)
   unsigned long long* trace;        // optional: [(step * 8 + phase) * grid + cta] %globaltimer at each phase boundary
 };
 

@@ -49,3 +49,24 @@ def test_editnet_forward_repeats():
     args = [b[k].cuda() for k in ("feats", "caps", "caplens", "prev", "prev_len")] + [False, 0.0]
     # the grouped GEMMs still reduce with floating-point atomics (order varies): noise at the 1e-7 level only
     assert _repeat(mod, args, 150) < 1e-5
+
+
+def test_editnet_forward_at_batch_64_is_bit_repeatable_through_the_persistent_kernel():
+    """B=64 (the benchmarked batch): the decode loop is the persistent step kernel, whose split-K partials meet in a
+    fixed order through distributed shared memory, and every time-batched GEMM has more tiles than SMs (no split-K):
+    no floating-point atomics anywhere on the forward path -> repeated forwards agree bit for bit."""
+    import ctypes as C
+    from show_edit_tell_b200 import _lib, editnet
+    V, D, A, Fd = 1003, 1024, 512, 2048
+    sd = EO.init_state_dict(V, D, D, D, A, Fd, seed=5)
+    mod = editnet.DecoderC(synth.word_map(V), D, D, D, A, Fd)
+    mod.load_state_dict(sd, strict=False)
+    mod = mod.cuda()
+    b = synth.make_batch(64, V, 36, Fd, 20, 18, ragged=True, seed=23)
+    args = [b[k].cuda() for k in ("feats", "caps", "caplens", "prev", "prev_len")] + [False, 0.0]
+    la, st = C.c_longlong(), C.c_longlong()
+    _lib.lib().set_step_stats(C.byref(la), C.byref(st), 1)
+    worst = _repeat(mod, args, 60)
+    _lib.lib().set_step_stats(C.byref(la), C.byref(st), 1)
+    assert la.value == 61, "the persistent decode-step kernel did not run (%d launches)" % la.value
+    assert worst == 0.0

@@ -57,8 +57,9 @@ print("  step total       %6.2f us" % float(dur[2:].sum(1).mean()))
 gate_of = {0: None, 1: 0, 2: 3, 3: 4, 4: 5}
 labels = ["gate seen", "first Q", "last Q", "accum ready", "ct0 staged", "staged(bar)", "arrives sent",
           "partners arrived", "finish done"]
-own = tr_[:, :7, 0]
-print("CTA 0 fine timeline, us after the gating barrier completed (mean over steps 2..):")
+cta = int(os.environ.get('SET_STEP_TRACE_CTA', '0'))
+own = tr_[:, :7, cta]
+print("CTA %d fine timeline, us after the gating barrier completed (mean over steps 2..):" % cta)
 for ph, nm in enumerate(["A", "B", "D", "E", "F"]):
     bar_idx = {0: 0, 1: 1, 2: 4, 3: 5, 4: 6}[ph]
     rows = []
