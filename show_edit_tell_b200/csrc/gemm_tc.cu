@@ -803,6 +803,300 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent kernel for the big time-batched GEMMs (>= one 128x128 tile per SM, plain epilogue, no split-K): one CTA
+// per SM walks the tile list (tile = blockIdx.x + k * gridDim.x over the concatenated tiles of the group's problems).
+// The K-block stream never stops at a tile boundary: the producer, the converters and the MMA issuer count K-blocks
+// ACROSS tiles, so the rings keep their phase and the first loads of tile n+1 are in flight while tile n still
+// multiplies.  The accumulator is double-buffered in tensor memory (2 x 128 columns + 4 operand slots of 64 columns =
+// all 512) and four dedicated warps drain tile n -- tensor memory -> a per-warp 32x32 staging block -> 128-byte
+// row segments in global memory -- while the MMA issuer is already into tile n+1.  Measured before this kernel
+// existed (tools/tc_kb_trace.py): the one-tile-per-CTA kernel spends 3 us in front of and 7 us behind a 35 us main
+// loop, and the two-CTAs-per-SM variant starves on its 2-deep Q ring (1800 cycles per K-block per CTA against 800 of
+// tensor-pipe work).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBigEpiWarps = 4;
+constexpr int kBigFirstEpiWarp = 2 + kConvWarps;
+constexpr int kBigThreads = 32 * (kBigFirstEpiWarp + kBigEpiWarps);
+struct BigCfg {
+  static constexpr int kNS = 4;                      // ring depth: raw P tiles, Q raw|lo tiles, tensor-memory operand slots
+  static_assert(kNS % kConvGroups == 0, "a converter group must revisit a slot on consecutive barrier phases");
+  static constexpr int kPBytes = kTileP * 128;
+  static constexpr int kQBytes = 128 * 128;
+  static constexpr int kQSlot = 2 * kQBytes;
+  static constexpr int kRingBytes = kNS * (kPBytes + kQSlot);
+  static constexpr int kEpiPitch = 36;               // floats per staged row: 16-byte aligned, conflict-free both ways
+  static constexpr int kEpiBytes = kBigEpiWarps * 32 * kEpiPitch * 4;
+  static constexpr int kSmemBytes = kRingBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_constant__ TcGroup<G> grp) {
+  using Cfg = BigCfg;
+  constexpr int NS = Cfg::kNS;
+  constexpr int QN = 128;
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_dyn + (base - smem_u32(smem_dyn));
+  const uint32_t q_base = base + NS * Cfg::kPBytes;
+  const uint32_t epi_base = base + Cfg::kRingBytes;
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
+  auto p_full = [&](int s) { return bar_base + 8u * s; };
+  auto q_full = [&](int s) { return bar_base + 8u * (NS + s); };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (2 * NS + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (3 * NS + s); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (4 * NS + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (4 * NS + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * NS + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = grp.cta_start[grp.n];
+
+  struct Tile { int pi, p0, q0, nkb; };
+  auto decode = [&](int t) {
+    Tile tl;
+    tl.pi = 0;
+    while (tl.pi + 1 < grp.n && t >= grp.cta_start[tl.pi + 1]) ++tl.pi;
+    const TcParams& prm = grp.p[tl.pi];
+    const int bid = t - grp.cta_start[tl.pi];
+    tl.q0 = (bid % prm.tiles_q) * QN;
+    tl.p0 = (bid / prm.tiles_q) * kTileP;
+    tl.nkb = 0;
+    for (int s = 0; s < prm.nseg; ++s) tl.nkb += (prm.K[s] + kBlockK - 1) / kBlockK;
+    return tl;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(p_full(s), 1);
+      mbar_init(q_full(s), 1);
+      mbar_init(conv_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full(a), 1);
+      mbar_init(acc_empty(a), kBigEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  const uint32_t tmem_ops = tmem_base + 2u * QN;   // operand slots behind the two accumulators
+
+  pdl_trigger();
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    pdl_wait();
+    uint32_t g = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const Tile tl = decode(t);
+      const TcParams& prm = grp.p[tl.pi];
+      for (int sg = 0; sg < prm.nseg; ++sg) {
+        const int nk = (prm.K[sg] + kBlockK - 1) / kBlockK;
+        for (int kb = 0; kb < nk; ++kb, ++g) {
+          const int s = (int)(g % NS);
+          if (g >= (uint32_t)NS) mbar_wait(empty_bar(s), ((g / NS) & 1u) ^ 1u);   // MMA of K-block g - NS retired
+          if (elect_one()) {
+            mbar_expect_tx(q_full(s), Cfg::kQBytes);
+            tma_load_2d(q_base + s * Cfg::kQSlot, &prm.mapQ[sg], q_full(s), kb * kBlockK, tl.q0);
+            mbar_expect_tx(p_full(s), Cfg::kPBytes);
+            tma_load_2d(base + s * Cfg::kPBytes, &prm.mapP[sg], p_full(s), kb * kBlockK, tl.p0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(kTileP >> 4) << 24);
+    uint32_t g = 0, tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      const Tile tl = decode(t);
+      const uint32_t ab = tc & 1u;
+      if (tc >= 2u) mbar_wait(acc_empty(ab), ((tc >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + ab * (uint32_t)QN;
+      for (int i = 0; i < tl.nkb; ++i, ++g) {
+        const int s = (int)(g % NS);
+        mbar_wait(conv_bar(s), (g / NS) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t q_hi = q_base + s * Cfg::kQSlot, q_lo = q_hi + Cfg::kQBytes;
+          const uint64_t b_hi0 = umma_desc(q_hi, 16u, 1024u), b_lo0 = umma_desc(q_lo, 16u, 1024u);
+          const uint32_t ta0 = tmem_ops + (uint32_t)s * 64u;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 8; ++k) {
+            const uint64_t b_hi = b_hi0 + (uint64_t)(2 * k), b_lo = b_lo0 + (uint64_t)(2 * k);
+            const uint32_t ta_hi = ta0 + (uint32_t)k * 8u;
+            umma_tf32_ts(acc, ta_hi + 32u, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);   // P_lo * Q_hi
+            umma_tf32_ts(acc, ta_hi, b_lo, idesc, 1u);                                 // P_hi * Q_lo
+            umma_tf32_ts(acc, ta_hi, b_hi, idesc, 1u);                                 // P_hi * Q_hi
+          }
+          umma_commit(empty_bar(s));
+          if (i == tl.nkb - 1) umma_commit(acc_full(ab));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kBigFirstEpiWarp) {
+    // ============================== converters ==============================
+    uint32_t total = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) total += (uint32_t)decode(t).nkb;
+    const int grp_id = (warp - 2) >> 2;
+    const int gt = (threadIdx.x - 64) & (kGT - 1);
+    auto split = [](float x, float& lo) { lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+    for (uint32_t g = (uint32_t)grp_id; g < total; g += kConvGroups) {
+      const int s = (int)(g % NS);
+      const uint32_t ph = (g / NS) & 1u;
+      // Q: the raw tile doubles as the hi operand (kind::tf32 ignores the low 13 mantissa bits); lo goes to the sibling
+      mbar_wait(q_full(s), ph);
+      const float4* q_hi = reinterpret_cast<const float4*>(gen_base + (q_base - base) + s * Cfg::kQSlot);
+      float4* q_lo = reinterpret_cast<float4*>(gen_base + (q_base - base) + s * Cfg::kQSlot + Cfg::kQBytes);
+#pragma unroll
+      for (int j = 0; j < Cfg::kQBytes / 16 / kGT; ++j) {
+        const float4 v = q_hi[gt + kGT * j];
+        float4 l;
+        split(v.x, l.x); split(v.y, l.y); split(v.z, l.z); split(v.w, l.w);
+        q_lo[gt + kGT * j] = l;
+      }
+      // P: tile row = tensor-memory lane; hi | lo as 2 x 32 columns of operand slot s
+      mbar_wait(p_full(s), ph);
+      const float4* p_raw = reinterpret_cast<const float4*>(gen_base + s * Cfg::kPBytes);
+      const int prow = (warp & 3) * 32 + lane;
+      const uint32_t ta = tmem_ops + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)s * 64u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 v = p_raw[prow * 8 + ((half * 4 + cc) ^ (prow & 7))];
+          float l;
+          split(v.x, l); hi[cc * 4 + 0] = __float_as_uint(v.x); lo[cc * 4 + 0] = __float_as_uint(l);
+          split(v.y, l); hi[cc * 4 + 1] = __float_as_uint(v.y); lo[cc * 4 + 1] = __float_as_uint(l);
+          split(v.z, l); hi[cc * 4 + 2] = __float_as_uint(v.z); lo[cc * 4 + 2] = __float_as_uint(l);
+          split(v.w, l); hi[cc * 4 + 3] = __float_as_uint(v.w); lo[cc * 4 + 3] = __float_as_uint(l);
+        }
+        tmem_st16(ta + (uint32_t)half * 16u, hi);
+        tmem_st16(ta + 32u + (uint32_t)half * 16u, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(conv_bar(s));
+    }
+  } else {
+    // ============================== epilogue ==============================
+    pdl_wait();   // C, `add` and c_row_len may be produced by the preceding kernels
+    const int quarter = warp & 3;   // tensor-memory lane quarter this warp may read
+    float* stg = reinterpret_cast<float*>(gen_base + (epi_base - base)) + (warp - kBigFirstEpiWarp) * 32 * Cfg::kEpiPitch;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;   // write-out: 8 lanes cover one 128-byte row segment
+    uint32_t tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      const Tile tl = decode(t);
+      const TcParams& prm = grp.p[tl.pi];
+      const uint32_t ab = tc & 1u;
+      const int m_lim = prm.Pr, n_lim = prm.Qr;
+      float* const Cp = prm.C;
+      const long ldc = prm.ldc, c_ld_inner = prm.c_ld_inner, ldadd = prm.ldadd;
+      const int c_inner = prm.c_inner, vin = prm.c_valid_inner, add_mod = prm.add_mod, beta = prm.beta, act = prm.act;
+      const int* row_len = prm.c_row_len;
+      const float* bias = prm.bias; const float* bias2 = prm.bias2; const float* add = prm.add;
+      auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+      const bool fast = al16(Cp) && ldc % 4 == 0 && (c_inner == 0 || c_ld_inner % 4 == 0) && al16(bias) && al16(bias2) &&
+                        al16(add) && ldadd % 4 == 0;
+      mbar_wait(acc_full(ab), (tc >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cb = 0; cb < QN / 32; ++cb) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * (uint32_t)QN + (uint32_t)(cb * 32), r);
+        if (cb == QN / 32 - 1) {   // the accumulator is in registers: hand it back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(ab));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(&stg[lane * Cfg::kEpiPitch + j]) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int n = tl.q0 + cb * 32 + c4;
+        const int nv = min(4, n_lim - n);
+        const int m0 = tl.p0 + quarter * 32 + rsub;   // this lane's rows: m0 + 4 * pass
+        auto row_ok = [&](int m) {
+          return m < m_lim && (row_len == nullptr || row_len[m % vin] > m / vin);
+        };
+        auto c_off = [&](int m) {
+          return (c_inner > 0 ? (long)(m / c_inner) * ldc + (long)(m % c_inner) * c_ld_inner : (long)m * ldc) + n;
+        };
+        if (fast && nv == 4) {
+          // every operand is 16-byte aligned: the 8 rows' reads of C (beta) and `add` go out together, one round trip
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b1 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n)) : z4;
+          const float4 b2 = bias2 ? __ldg(reinterpret_cast<const float4*>(bias2 + n)) : z4;
+          float4 ov[8], av[8];
+          long off[8];
+          unsigned okm = 0u;
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int m = m0 + 4 * pass;
+            const bool ok = row_ok(m);
+            okm |= ok ? (1u << pass) : 0u;
+            off[pass] = ok ? c_off(m) : 0;
+            ov[pass] = (ok && beta) ? *reinterpret_cast<const float4*>(Cp + off[pass]) : z4;
+            av[pass] = (ok && add) ? *reinterpret_cast<const float4*>(add + (long)(add_mod ? m % add_mod : m) * ldadd + n) : z4;
+          }
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            if (!((okm >> pass) & 1u)) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(&stg[(pass * 4 + rsub) * Cfg::kEpiPitch + c4]);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (bias) { v[0] += b1.x; v[1] += b1.y; v[2] += b1.z; v[3] += b1.w; }
+            if (bias2) { v[0] += b2.x; v[1] += b2.y; v[2] += b2.z; v[3] += b2.w; }
+            if (add) { v[0] += av[pass].x; v[1] += av[pass].y; v[2] += av[pass].z; v[3] += av[pass].w; }
+            if (act == 1) { for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.f); }
+            else if (act == 2) { for (int k = 0; k < 4; ++k) v[k] = tanhf(v[k]); }
+            if (beta) { v[0] += ov[pass].x; v[1] += ov[pass].y; v[2] += ov[pass].z; v[3] += ov[pass].w; }
+            *reinterpret_cast<float4*>(Cp + off[pass]) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else if (nv > 0) {
+          // ragged right edge or unaligned operands: element-wise
+#pragma unroll 1
+          for (int pass = 0; pass < 8; ++pass) {
+            const int m = m0 + 4 * pass;
+            if (!row_ok(m)) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(&stg[(pass * 4 + rsub) * Cfg::kEpiPitch + c4]);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            float* cp = Cp + c_off(m);
+            const float* ap = add ? add + (long)(add_mod ? m % add_mod : m) * ldadd + n : nullptr;
+            for (int k = 0; k < nv; ++k) {
+              float x = v[k];
+              if (bias) x += __ldg(bias + n + k);
+              if (bias2) x += __ldg(bias2 + n + k);
+              if (ap) x += ap[k];
+              if (act == 1) x = fmaxf(x, 0.f);
+              else if (act == 2) x = tanhf(x);
+              cp[k] = beta ? cp[k] + x : x;
+            }
+          }
+        }
+        __syncwarp();   // the staging block is rewritten by the next column block
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -838,6 +1132,8 @@ void tc_init(TcDevice* d, int dev) {
   set_attr(gemm_tc_kernel<64, 8>, TcCfg<64>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8>, TcCfg<128>::kSmemBytes);
   set_attr(gemm_tc_kernel<128, 1, 1>, TcCfg<128, 1>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 2, 1>, TcCfg<128, 1>::kSmemBytes);
   set_attr(gemm_tc_kernel<128, 5, 1>, TcCfg<128, 1>::kSmemBytes);  set_attr(gemm_tc_kernel<128, 8, 1>, TcCfg<128, 1>::kSmemBytes);
+  set_attr(gemm_big_kernel<1>, BigCfg::kSmemBytes);  set_attr(gemm_big_kernel<2>, BigCfg::kSmemBytes);
+  set_attr(gemm_big_kernel<5>, BigCfg::kSmemBytes);  set_attr(gemm_big_kernel<8>, BigCfg::kSmemBytes);
   ok = ok && cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
   for (int c = 2; ok && c <= 8; c <<= 1) {
     cudaLaunchConfig_t cfg;
@@ -1111,6 +1407,15 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
       return launch_chain_cluster(gemm_tc_kernel<128, G>, dim3(cta), dim3(kThreadsTc), TcCfg<128>::kSmemBytes, stream, cluster, small);
     }
     if (QN == 64) return launch_chain(gemm_tc_kernel<64, G>, dim3(cta), dim3(kThreadsTc), TcCfg<64>::kSmemBytes, stream, small);
+    // plain 128x128-tile problems without split-K: the persistent kernel (one CTA per SM walks the tile list, the
+    // epilogue of a tile overlaps the main loop of the next).  SET_TC_BIG=0 restores the one-tile-per-CTA kernels.
+    static const int big_on = getenv("SET_TC_BIG") ? atoi(getenv("SET_TC_BIG")) : 1;
+    bool big_ok = big_on != 0;
+    for (int k = 0; k < grp.n; ++k)
+      big_ok = big_ok && !grp.p[k].fused && grp.p[k].split_k == 1 && !grp.p[k].swap && grp.p[k].nblk == 1;
+    if (big_ok && (++g_tc_twin_launches, true))
+      return launch_chain(gemm_big_kernel<G>, dim3(cta < g_sm_count ? cta : g_sm_count), dim3(kBigThreads),
+                          BigCfg::kSmemBytes, stream, small);
     // many tiles per SM and no fused epilogue in play: two CTAs per SM (see TcCfg)
     static const int twin_on = getenv("SET_TC_TWIN") ? atoi(getenv("SET_TC_TWIN")) : 1;
     bool any_fused = false;

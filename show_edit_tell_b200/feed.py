@@ -103,6 +103,20 @@ def collate_adaptive(data, root=".", max_regions=100, feat_dim=2048, pin=None):
             torch.stack(prev_caplen, 0), torch.stack(all_captions, 0))
 
 
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    """One copy stream per device for the life of the process: the caching allocator keeps a block pool per stream, so
+    a fresh stream per prefetcher (one per epoch) would cudaMalloc its double buffer again each time -- measured on
+    B200: 2-13 ms in front of the first step of every new iterator."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _copy_streams.get(idx)
+    if st is None:
+        st = _copy_streams[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
 class DevicePrefetcher:
     """Iterate `loader` (host batches: tuples of tensors) one batch ahead: while the consumer computes on batch i, the
     tensors of batch i+1 travel host->device on a copy stream into the other half of a double buffer.  Pinned source
@@ -114,7 +128,7 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         self.host_batch = None      # the host tensors of the batch handed out last (lengths stay useful on the host)
         self.cuda = self.device.type == "cuda"
-        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.stream = _copy_stream(self.device) if self.cuda else None
 
     def _stage(self, batch):
         if not self.cuda:
