@@ -350,13 +350,18 @@ SET_API int set_beam_finalize(int N, int K, int Lmax, int steps_done, const int*
                               const int64_t* complete_seqs, const int* complete_len, int64_t* out_seq, int* out_len,
                               float* out_score, void* stream);
 
-/* Data-parallel overlap (new: the reference is single-process).  Arms the NEXT set_editnet_xe_backward /
- * set_editnet_rollout_backward call of this thread: when every parameter gradient except those of embed.*,
- * caption_encoder.* and visual_attention.att_embed / features_att is final (about two thirds into the reverse pass:
- * before the visual feature path and the encoder BPTT), the call records an event on its stream and makes `comm_stream`
- * wait for it.  An all-reduce of those gradients enqueued on `comm_stream` after the call returns overlaps the rest of
- * the pass (the Python side keeps them contiguous in its flat buffer). */
-SET_API int set_backward_bucket_notify(void* comm_stream);
+/* Data-parallel overlap (new: the reference is single-process).  The reverse pass finishes the parameter gradients in
+ * four groups ("buckets"), in this order:
+ *   0  fc.*                                                          before the per-step loop
+ *   1  attention_lstm.*, copy_lstm.*, caption_attention.cap_features_att.*   after the loop (big weight-gradient groups)
+ *   2  embed.*, caption_encoder.*                                    input-gradient tail, encoder BPTT
+ *   3  everything else (caption / visual attention), final when the call returns.
+ * `events` = n <= 8 cudaEvent_t handles.  Arms the NEXT set_editnet_xe_backward / set_editnet_rollout_backward call of
+ * this thread: the call records events[k] on its stream as soon as bucket k is final (events of buckets the call does
+ * not know, and every event not recorded earlier, are recorded at its end).  A communication stream that waits for
+ * events[k] before all-reducing bucket k overlaps the collective with the rest of the pass; the Python side
+ * (train.XETrainer) keeps each bucket contiguous in its flat gradient buffer. */
+SET_API int set_backward_bucket_events(void* const* events, int n);
 /* persistent decode-step kernel (csrc/step_kernel.cu): launches since the last reset and the timesteps they covered
    (0 launches: the shape fell outside the persistent path and the per-step launch chain ran) */
 SET_API int set_step_stats(long long* launches, long long* steps, int reset);

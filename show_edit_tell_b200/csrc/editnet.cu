@@ -592,24 +592,31 @@ int steps_persistent(Ctx& c, const float* feats, int t0, int nt, const int* bt, 
 }
 
 // ------------------------------------------------------------------------ reverse pass
-// Data-parallel overlap: every parameter gradient except those of the embedding table, the caption encoder and
-// att_embed / features_att -- 265 of 355 MB, laid out as one contiguous range by the Python side -- is final about two
-// thirds of the way through the reverse pass (before the visual feature path and the encoder BPTT).  When armed (set_backward_bucket_notify), backward_core records an event at that point
-// and makes the caller's communication stream wait for it: an all-reduce of the tail enqueued on that stream right
-// after the backward call returns then runs underneath the rest of the reverse pass.
-thread_local cudaStream_t g_bucket_stream = nullptr;
-thread_local bool g_bucket_armed = false;
-int bucket_notify(cudaStream_t st) {
-  if (!g_bucket_armed) return SET_OK;
-  g_bucket_armed = false;
-  static thread_local cudaEvent_t ev[64] = {nullptr};
-  int dev = 0;
-  SET_CHECK_CUDA(cudaGetDevice(&dev));
-  SET_REQUIRE(dev >= 0 && dev < 64, "device ordinal");
-  if (!ev[dev]) SET_CHECK_CUDA(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
-  SET_CHECK_CUDA(cudaEventRecord(ev[dev], st));
-  SET_CHECK_CUDA(cudaStreamWaitEvent(g_bucket_stream, ev[dev], 0));
+// Data-parallel overlap.  The reverse pass finishes the parameter gradients in four groups, in this order -- the
+// Python side lays the flat gradient buffer out in the same order, one contiguous range ("bucket") per group:
+//   0  fc.*                                                   before the per-step loop (needs only d logits and the dropped h2)
+//   1  attention_lstm.*, copy_lstm.*, cap_features_att.*      after the loop: the two big weight-gradient groups
+//   2  embed.*, caption_encoder.*                             input-gradient tail + encoder BPTT
+//   3  caption / visual attention                             last (third weight-gradient group + visual feature path)
+// When armed (set_backward_bucket_events), backward_core records the caller's event k on its stream as soon as
+// bucket k is final; the caller's communication stream waits for event k and all-reduces bucket k underneath the
+// rest of the pass.  Only the last bucket (39 of 355 MB) is reduced after the pass.
+constexpr int kMaxBuckets = 8;
+thread_local cudaEvent_t g_bucket_ev[kMaxBuckets];
+thread_local int g_bucket_n = 0;       // events armed for the next reverse pass
+thread_local int g_bucket_next = 0;    // first event not yet recorded
+int bucket_notify(int k, cudaStream_t st) {
+  // events are recorded in order: bucket k final implies every earlier bucket is final (or absent in this path)
+  while (g_bucket_next <= k && g_bucket_next < g_bucket_n) {
+    SET_CHECK_CUDA(cudaEventRecord(g_bucket_ev[g_bucket_next], st));
+    ++g_bucket_next;
+  }
   return SET_OK;
+}
+int bucket_finish(cudaStream_t st) {   // end of the pass: whatever was not signalled is final now; disarm
+  const int r = bucket_notify(kMaxBuckets, st);
+  g_bucket_n = g_bucket_next = 0;
+  return r;
 }
 
 struct DLogits {
@@ -625,6 +632,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   Ws& s = c.ws;
   cudaStream_t st = c.st;
   const int TB = T * B;
+  struct BucketGuard { ~BucketGuard() { g_bucket_n = g_bucket_next = 0; } } bucket_guard;   // an error return disarms too
   SET_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(s.emb_prev) + s.regionB_begin, 0,
                                  s.regionB_end - s.regionB_begin, st));
   // The dX pass contracts over a weight's OUTPUT features.  The tensor-core kernel wants both operands
@@ -652,12 +660,71 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     else gemm_add_seg(p, dY, ldy, W + c0, I, O);
     p.w_const = 1;   // W / W^T are not written again before the optimizer step
   };
+  // ---- time-batched tail: weight gradients (dY^T X over all T*B rows; undecoded rows are zero)
+  // With the tensor-core engine dW = dY^T X is issued in NT form on explicit transposes of the two
+  // activation matrices (K-major operands only, see the note on W^T above); each distinct matrix is
+  // transposed once per backward call into `tscratch`.
+  struct TrEntry { const float* src; long ld; int rows, cols; const float* dst; };
+  std::vector<TrEntry> tr_cache;
+  std::vector<TrJob> tr_pending;
+  size_t tr_used = 0;
+  int tr_err = SET_OK;
+  auto TR = [&](const float* X, long ld, int rows, int cols) -> const float* {
+    for (const auto& e : tr_cache)
+      if (e.src == X && e.ld == ld && e.rows == rows && e.cols == cols) return e.dst;
+    const size_t rp = ((size_t)rows + 3) & ~size_t(3);
+    if (tr_used + rp * cols > s.tscratch_floats) { tr_err = SET_ERR_WORKSPACE; return nullptr; }
+    float* dst = s.tscratch + tr_used;
+    tr_used += rp * cols;
+    tr_pending.push_back(TrJob{X, ld, dst, (long)rp, rows, cols, 0, 0});   // launched by flush_tr(), batched
+    tr_cache.push_back({X, ld, rows, cols, dst});
+    return dst;
+  };
+  auto flush_tr = [&]() -> int {
+    if (tr_pending.empty()) return SET_OK;
+    const int r = transpose_batch(tr_pending.data(), (int)tr_pending.size(), st);
+    tr_pending.clear();
+    return r;
+  };
+  const int dwm = use_wt ? kNT : kTN;
+  auto TN = [&](float* C, long ldc, int M, int N, const float* dY, long ldy, const float* X, long ldx, int K) {
+    GemmProblem p = gemm_problem(M, N, C, ldc);
+    if (use_wt) {
+      const long rp = ((long)K + 3) & ~3L;
+      gemm_add_seg(p, TR(dY, ldy, K, M), rp, TR(X, ldx, K, N), rp, K);
+    } else {
+      gemm_add_seg(p, dY, ldy, X, ldx, K);
+    }
+    p.beta = 1;
+    return p;
+  };
   {  // d(dropout(h2)) for every step at once: dlogits @ fc.weight
     GemmProblem p = gemm_problem(TB, D, s.dh2raw, D);
     dx(p, dl.p, dl.ld, w.fc_w, s.t_fc, V, D, 0);
     p.a_inner = dl.inner; p.a_ld_inner = dl.ld_inner; p.a_row_len = dl.row_len; p.a_valid_inner = B;
     p.w_const = 0;   // directly follows the kernels that write W^T
     SET_PROPAGATE(gemm(dxm, p, st));
+  }
+  {  // bucket 0: fc.* needs only d logits and the dropped h2 -- first, so that its all-reduce runs under the per-step loop
+    const bool dl_plain = (dl.inner == 0 && dl.row_len == nullptr);   // time-major d logits (trainer / rollout)
+    if (dl_plain) {
+      GemmProblem p = TN(g.fc_w, D, V, D, dl.p, dl.ld, s.h2drop, D, TB);
+      SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
+      SET_PROPAGATE(flush_tr());
+      SET_PROPAGATE(gemm(dwm, p, st));
+      SET_PROPAGATE(colsum(dl.p, dl.ld, TB, V, g.fc_b, 1, st));
+    } else {
+      // batch-major upstream gradient (autograd drop-in path): strided, masked rows -> CUDA-core TN kernel
+      GemmProblem q[2];
+      for (int k = 0; k < 2; ++k) {
+        q[k] = k == 0 ? gemm_problem(V, D, g.fc_w, D) : gemm_problem(V, 1, g.fc_b, 1);
+        gemm_add_seg(q[k], dl.p, dl.ld, k == 0 ? s.h2drop : s.ones, k == 0 ? D : 1, TB);
+        q[k].beta = 1;
+        q[k].a_inner = dl.inner; q[k].a_ld_inner = dl.ld_inner; q[k].a_row_len = dl.row_len; q[k].a_valid_inner = B;
+      }
+      SET_PROPAGATE(gemm_group(kTN, q, 2, st));
+    }
+    SET_PROPAGATE(bucket_notify(0, st));
   }
   SET_PROPAGATE(profile_mark(2, st));
   bool copy2_done = false;
@@ -770,8 +837,47 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     }
   }
   SET_PROPAGATE(profile_mark(3, st));
+  // ---- time-batched tail.  Order = the order in which the data-parallel step wants the gradient buckets: the two big
+  // weight-gradient groups first (their all-reduce then runs under everything that follows), the input-gradient tail and
+  // the encoder BPTT -- a chain of small kernels that leaves most SMs to the collective -- next, the attention
+  // weights and the visual feature path last.
+  SET_PROPAGATE(sum_time(s.dG1, s.sumG1, T, (long)B * 4 * D, st));   // (first: a weight-gradient operand and the d final_hidden source)
+  {  // every bias gradient that is a column sum of a per-step buffer
+    const ColJob cj[] = {
+        {s.dG1, 4L * D, TB, 4 * D, g.al_bih, 0, 0},        {s.dG1, 4L * D, TB, 4 * D, g.al_bhh, 0, 0},
+        {s.dG2, 4L * D, TB, 4 * D, g.cl_x2h_b, 0, 0},      {s.dG2, 4L * D, TB, 4 * D, g.cl_h2h_b, 0, 0},
+        {s.dS2, (long)LS2, TB, A, g.ca_dec_b, 0, 0},        {s.dS2 + A, (long)LS2, TB, A, g.va_dec_b, 0, 0},
+        {s.dS2 + 2 * A, (long)LS2, TB, D, g.ca_gate_b, 0, 0}, {s.dS2 + 2 * A + D, (long)LS2, TB, D, g.ca_tc_b, 0, 0},
+        {s.dsc, (long)D, TB, D, g.ca_sc_b, 0, 0},           {s.dK, (long)D, TB, D, g.cl_gcn_b, 0, 0},
+        {s.dK, (long)D, TB, D, g.cl_gcm_b, 0, 0},           {s.datt1c, (long)A, B * P, A, g.ca_feat_b, 0, 0}};
+    SET_PROPAGATE(colsum_batch(cj, (int)(sizeof(cj) / sizeof(cj[0])), st));
+  }
+  // weight gradients (dY^T X over all T*B rows; undecoded rows are zero), one group per bucket
+  {
+    GemmProblem p[8];
+    int n = 0;
+    if (T > 1) p[n++] = TN(g.al_whh, D, 4 * D, D, s.dG1 + (size_t)B * 4 * D, 4 * D, s.X2, LX2, (T - 1) * B);
+    p[n++] = TN(g.al_wih, 3 * D + F, 4 * D, D, s.dG1, 4 * D, s.emb_all, D, TB);
+    p[n++] = TN(g.al_wih + D, 3 * D + F, 4 * D, D, s.sumG1, 4 * D, s.fh, D, B);
+    p[n++] = TN(g.al_wih + 2 * D, 3 * D + F, 4 * D, D, s.dG1, 4 * D, s.h2, D, TB);
+    p[n++] = TN(g.al_wih + 3 * D, 3 * D + F, 4 * D, F, s.sumG1, 4 * D, s.image_mean, F, B);
+    SET_PROPAGATE(flush_tr());
+    SET_PROPAGATE(gemm_group(dwm, p, n, st));
+  }
+  {
+    GemmProblem p[8];
+    int n = 0;
+    p[n++] = TN(g.cl_x2h_w, LX2, 4 * D, LX2, s.dG2, 4 * D, s.X2, LX2, TB);
+    p[n++] = TN(g.cl_h2h_w, D, 4 * D, D, s.dG2, 4 * D, s.h2, D, TB);
+    p[n++] = TN(g.cl_gcn_w, D, D, D, s.dK, D, s.cnew, D, TB);
+    p[n++] = TN(g.cl_gcm_w, D, D, D, s.dK, D, s.sel, D, TB);
+    p[n++] = TN(g.ca_feat_w, D, A, D, s.datt1c, A, s.prev_h, D, B * P);
+    SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
+    SET_PROPAGATE(flush_tr());
+    SET_PROPAGATE(gemm_group(dwm, p, n, st));
+  }
+  SET_PROPAGATE(bucket_notify(1, st));   // attention_lstm.*, copy_lstm.*, cap_features_att.* final
   // ---- time-batched tail: input gradients
-  SET_PROPAGATE(sum_time(s.dG1, s.sumG1, T, (long)B * 4 * D, st));
   {
     GemmProblem p[2];
     p[0] = gemm_problem(B, D, s.dfh, D);                      // d final_hidden
@@ -784,140 +890,11 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   }
   SET_PROPAGATE(embed_bwd(caps_tok, tok_ld, tok_os, s.emb_all, s.demb_all, g.embed, V, T, B, D, c.s.train,
                           dec_len_dev, st));
-  // ---- time-batched tail: weight gradients (dY^T X over all T*B rows; undecoded rows are zero)
-  // With the tensor-core engine dW = dY^T X is issued in NT form on explicit transposes of the two
-  // activation matrices (K-major operands only, see the note on W^T above); each distinct matrix is
-  // transposed once per backward call into `tscratch`.
-  struct TrEntry { const float* src; long ld; int rows, cols; const float* dst; };
-  std::vector<TrEntry> tr_cache;
-  std::vector<TrJob> tr_pending;
-  size_t tr_used = 0;
-  int tr_err = SET_OK;
-  auto TR = [&](const float* X, long ld, int rows, int cols) -> const float* {
-    for (const auto& e : tr_cache)
-      if (e.src == X && e.ld == ld && e.rows == rows && e.cols == cols) return e.dst;
-    const size_t rp = ((size_t)rows + 3) & ~size_t(3);
-    if (tr_used + rp * cols > s.tscratch_floats) { tr_err = SET_ERR_WORKSPACE; return nullptr; }
-    float* dst = s.tscratch + tr_used;
-    tr_used += rp * cols;
-    tr_pending.push_back(TrJob{X, ld, dst, (long)rp, rows, cols, 0, 0});   // launched by flush_tr(), batched
-    tr_cache.push_back({X, ld, rows, cols, dst});
-    return dst;
-  };
-  auto flush_tr = [&]() -> int {
-    if (tr_pending.empty()) return SET_OK;
-    const int r = transpose_batch(tr_pending.data(), (int)tr_pending.size(), st);
-    tr_pending.clear();
-    return r;
-  };
-  const int dwm = use_wt ? kNT : kTN;
-  auto TN = [&](float* C, long ldc, int M, int N, const float* dY, long ldy, const float* X, long ldx, int K) {
-    GemmProblem p = gemm_problem(M, N, C, ldc);
-    if (use_wt) {
-      const long rp = ((long)K + 3) & ~3L;
-      gemm_add_seg(p, TR(dY, ldy, K, M), rp, TR(X, ldx, K, N), rp, K);
-    } else {
-      gemm_add_seg(p, dY, ldy, X, ldx, K);
-    }
-    p.beta = 1;
-    return p;
-  };
-  {
-    GemmProblem p[8];
-    int n = 0;
-    if (T > 1) p[n++] = TN(g.al_whh, D, 4 * D, D, s.dG1 + (size_t)B * 4 * D, 4 * D, s.X2, LX2, (T - 1) * B);
-    p[n++] = TN(g.al_wih, 3 * D + F, 4 * D, D, s.dG1, 4 * D, s.emb_all, D, TB);
-    p[n++] = TN(g.al_wih + D, 3 * D + F, 4 * D, D, s.sumG1, 4 * D, s.fh, D, B);
-    p[n++] = TN(g.al_wih + 2 * D, 3 * D + F, 4 * D, D, s.dG1, 4 * D, s.h2, D, TB);
-    p[n++] = TN(g.al_wih + 3 * D, 3 * D + F, 4 * D, F, s.sumG1, 4 * D, s.image_mean, F, B);
-    p[n++] = TN(g.cl_x2h_w, LX2, 4 * D, LX2, s.dG2, 4 * D, s.X2, LX2, TB);
-    p[n++] = TN(g.cl_h2h_w, D, 4 * D, D, s.dG2, 4 * D, s.h2, D, TB);
-    SET_PROPAGATE(flush_tr());
-    SET_PROPAGATE(gemm_group(dwm, p, n, st));
-  }
-  {
-    GemmProblem p[8];
-    int n = 0;
-    p[n++] = TN(g.ca_dec_w, D, A, D, s.dS2, LS2, s.X2, LX2, TB);
-    p[n++] = TN(g.va_dec_w, D, A, D, s.dS2 + A, LS2, s.X2, LX2, TB);
-    p[n++] = TN(g.ca_gate_w, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.emb_all, D, TB);
-    p[n++] = TN(g.ca_gate_w + D, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.X2, LX2, TB);
-    p[n++] = TN(g.ca_gate_w + 2 * D, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.ctx_c, D, TB);
-    p[n++] = TN(g.ca_sc_w, D, D, D, s.dsc, D, s.ctx_c, D, TB);
-    p[n++] = TN(g.ca_tc_w, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.emb_all, D, TB);
-    p[n++] = TN(g.ca_tc_w + D, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.X2, LX2, TB);
-    SET_PROPAGATE(flush_tr());
-    SET_PROPAGATE(gemm_group(dwm, p, n, st));
-  }
-  {
-    GemmProblem p[8];
-    int n = 0;
-    p[n++] = TN(g.cl_gcn_w, D, D, D, s.dK, D, s.cnew, D, TB);
-    p[n++] = TN(g.cl_gcm_w, D, D, D, s.dK, D, s.sel, D, TB);
-    p[n++] = TN(g.ca_feat_w, D, A, D, s.datt1c, A, s.prev_h, D, B * P);
-    const bool dl_plain = (dl.inner == 0 && dl.row_len == nullptr);   // time-major d logits (trainer / rollout)
-    if (dl_plain) p[n++] = TN(g.fc_w, D, V, D, dl.p, dl.ld, s.h2drop, D, TB);
-    SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
-    SET_PROPAGATE(flush_tr());
-    SET_PROPAGATE(gemm_group(dwm, p, n, st));
-    if (dl_plain) {
-      SET_PROPAGATE(colsum(dl.p, dl.ld, TB, V, g.fc_b, 1, st));
-    } else {
-      // batch-major upstream gradient (autograd drop-in path): strided, masked rows -> CUDA-core TN kernel
-      GemmProblem q[2];
-      for (int k = 0; k < 2; ++k) {
-        q[k] = k == 0 ? gemm_problem(V, D, g.fc_w, D) : gemm_problem(V, 1, g.fc_b, 1);
-        gemm_add_seg(q[k], dl.p, dl.ld, k == 0 ? s.h2drop : s.ones, k == 0 ? D : 1, TB);
-        q[k].beta = 1;
-        q[k].a_inner = dl.inner; q[k].a_ld_inner = dl.ld_inner; q[k].a_row_len = dl.row_len; q[k].a_valid_inner = B;
-      }
-      SET_PROPAGATE(gemm_group(kTN, q, 2, st));
-    }
-  }
-  {
-    const ColJob cj[] = {
-        {s.dG1, 4L * D, TB, 4 * D, g.al_bih, 0, 0},        {s.dG1, 4L * D, TB, 4 * D, g.al_bhh, 0, 0},
-        {s.dG2, 4L * D, TB, 4 * D, g.cl_x2h_b, 0, 0},      {s.dG2, 4L * D, TB, 4 * D, g.cl_h2h_b, 0, 0},
-        {s.dS2, (long)LS2, TB, A, g.ca_dec_b, 0, 0},        {s.dS2 + A, (long)LS2, TB, A, g.va_dec_b, 0, 0},
-        {s.dS2 + 2 * A, (long)LS2, TB, D, g.ca_gate_b, 0, 0}, {s.dS2 + 2 * A + D, (long)LS2, TB, D, g.ca_tc_b, 0, 0},
-        {s.dsc, (long)D, TB, D, g.ca_sc_b, 0, 0},           {s.dK, (long)D, TB, D, g.cl_gcn_b, 0, 0},
-        {s.dK, (long)D, TB, D, g.cl_gcm_b, 0, 0},           {s.datt1c, (long)A, B * P, A, g.ca_feat_b, 0, 0}};
-    SET_PROPAGATE(colsum_batch(cj, (int)(sizeof(cj) / sizeof(cj[0])), st));
-  }
-  // final from here on: everything but embed.*, caption_encoder.*, visual_attention.att_embed / features_att
-  SET_PROPAGATE(bucket_notify(st));
   {  // d prev_h also flows through cap_features_att
     GemmProblem p = gemm_problem(B * P, D, s.dprev_h, D);
     dx(p, s.datt1c, A, w.ca_feat_w, s.t_ca_feat, A, D, 0);
     p.beta = 1;
     SET_PROPAGATE(gemm(dxm, p, st));
-  }
-  // ---- visual feature path
-  if (c.s.train) {
-    const int TBR = T * B * R;
-    GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_t, D, TBR);
-    SET_PROPAGATE(flush_tr());
-    SET_PROPAGATE(gemm(dwm, pw, st));
-    SET_PROPAGATE(colsum(s.datt1, A, TBR, A, g.va_feat_b, 1, st));
-    GemmProblem px = gemm_problem(TBR, D, s.dfe_t, D);
-    dx(px, s.datt1, A, w.va_feat_w, s.t_va_feat, A, D, 0);
-    SET_PROPAGATE(gemm(dxm, px, st));
-    SET_PROPAGATE(vis_dropout_bwd(s.fe_pre, s.dfe_t, s.dfe_pre, dec_len_dev, T, B, R, D, c.seed, st));
-  } else {
-    GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_pre, D, B * R);
-    SET_PROPAGATE(flush_tr());
-    SET_PROPAGATE(gemm(dwm, pw, st));
-    SET_PROPAGATE(colsum(s.datt1, A, B * R, A, g.va_feat_b, 1, st));
-    GemmProblem px = gemm_problem(B * R, D, s.dfe_pre, D);
-    dx(px, s.datt1, A, w.va_feat_w, s.t_va_feat, A, D, 0);
-    SET_PROPAGATE(gemm(dxm, px, st));
-    SET_PROPAGATE(relu_bwd_inplace(s.dfe_pre, s.fe_pre, (long)B * R * D, st));
-  }
-  {
-    GemmProblem pw = TN(g.va_emb_w, F, D, F, s.dfe_pre, D, feats, F, B * R);
-    SET_PROPAGATE(flush_tr());
-    SET_PROPAGATE(gemm(dwm, pw, st));
-    SET_PROPAGATE(colsum(s.dfe_pre, D, B * R, D, g.va_emb_b, 1, st));
   }
   // ---- caption encoder BPTT (reverse of editnet.py:333-341)
   SET_PROPAGATE(tanh_bwd_inplace(s.dfh, s.fh, (long)B * D, st));
@@ -968,7 +945,50 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     SET_PROPAGATE(gemm(dxm, px, st));
     SET_PROPAGATE(embed_bwd(prev, c.s.Wp, 1, s.emb_prev, s.demb_prev, g.embed, V, P, B, D, c.s.train, nullptr, st));
   }
+  SET_PROPAGATE(bucket_notify(2, st));   // embed.*, caption_encoder.* final
+  {
+    GemmProblem p[8];
+    int n = 0;
+    p[n++] = TN(g.ca_dec_w, D, A, D, s.dS2, LS2, s.X2, LX2, TB);
+    p[n++] = TN(g.va_dec_w, D, A, D, s.dS2 + A, LS2, s.X2, LX2, TB);
+    p[n++] = TN(g.ca_gate_w, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.emb_all, D, TB);
+    p[n++] = TN(g.ca_gate_w + D, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.X2, LX2, TB);
+    p[n++] = TN(g.ca_gate_w + 2 * D, 3 * D, D, D, s.dS2 + 2 * A, LS2, s.ctx_c, D, TB);
+    p[n++] = TN(g.ca_sc_w, D, D, D, s.dsc, D, s.ctx_c, D, TB);
+    p[n++] = TN(g.ca_tc_w, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.emb_all, D, TB);
+    p[n++] = TN(g.ca_tc_w + D, 2 * D, D, D, s.dS2 + 2 * A + D, LS2, s.X2, LX2, TB);
+    SET_PROPAGATE(flush_tr());
+    SET_PROPAGATE(gemm_group(dwm, p, n, st));
+  }
+  // ---- visual feature path
+  if (c.s.train) {
+    const int TBR = T * B * R;
+    GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_t, D, TBR);
+    SET_PROPAGATE(flush_tr());
+    SET_PROPAGATE(gemm(dwm, pw, st));
+    SET_PROPAGATE(colsum(s.datt1, A, TBR, A, g.va_feat_b, 1, st));
+    GemmProblem px = gemm_problem(TBR, D, s.dfe_t, D);
+    dx(px, s.datt1, A, w.va_feat_w, s.t_va_feat, A, D, 0);
+    SET_PROPAGATE(gemm(dxm, px, st));
+    SET_PROPAGATE(vis_dropout_bwd(s.fe_pre, s.dfe_t, s.dfe_pre, dec_len_dev, T, B, R, D, c.seed, st));
+  } else {
+    GemmProblem pw = TN(g.va_feat_w, D, A, D, s.datt1, A, s.fe_pre, D, B * R);
+    SET_PROPAGATE(flush_tr());
+    SET_PROPAGATE(gemm(dwm, pw, st));
+    SET_PROPAGATE(colsum(s.datt1, A, B * R, A, g.va_feat_b, 1, st));
+    GemmProblem px = gemm_problem(B * R, D, s.dfe_pre, D);
+    dx(px, s.datt1, A, w.va_feat_w, s.t_va_feat, A, D, 0);
+    SET_PROPAGATE(gemm(dxm, px, st));
+    SET_PROPAGATE(relu_bwd_inplace(s.dfe_pre, s.fe_pre, (long)B * R * D, st));
+  }
+  {
+    GemmProblem pw = TN(g.va_emb_w, F, D, F, s.dfe_pre, D, feats, F, B * R);
+    SET_PROPAGATE(flush_tr());
+    SET_PROPAGATE(gemm(dwm, pw, st));
+    SET_PROPAGATE(colsum(s.dfe_pre, D, B * R, D, g.va_emb_b, 1, st));
+  }
   SET_REQUIRE(tr_err == SET_OK, "transpose scratch exhausted");
+  SET_PROPAGATE(bucket_finish(st));
   return SET_OK;
 }
 
@@ -1325,9 +1345,14 @@ int set_step_stats(long long* launches, long long* steps, int reset) {
   return SET_OK;
 }
 
-int set_backward_bucket_notify(void* comm_stream) {
-  g_bucket_stream = reinterpret_cast<cudaStream_t>(comm_stream);
-  g_bucket_armed = true;
+int set_backward_bucket_events(void* const* events, int n) {
+  SET_REQUIRE(n >= 0 && n <= kMaxBuckets && (n == 0 || events), "0..8 events");
+  for (int k = 0; k < n; ++k) {
+    SET_REQUIRE(events[k], "null event");
+    g_bucket_ev[k] = reinterpret_cast<cudaEvent_t>(events[k]);
+  }
+  g_bucket_n = n;
+  g_bucket_next = 0;
   return SET_OK;
 }
 

@@ -814,6 +814,12 @@ __global__ void __launch_bounds__(kThreadsTc, TWIN ? 2 : 1) gemm_tc_kernel(const
 // existed (tools/tc_kb_trace.py): the one-tile-per-CTA kernel spends 3 us in front of and 7 us behind a 35 us main
 // loop, and the two-CTAs-per-SM variant starves on its 2-deep Q ring (1800 cycles per K-block per CTA against 800 of
 // tensor-pipe work).
+// Tiles are handed out dynamically (when there are more tiles than CTAs): the producer warp draws tiles from a
+// global counter (one atomic per tile, issued a tile ahead) and publishes it to the other warps through a 4-deep ring
+// in shared memory.  A static stride would tie the kernel's duration to its slowest CTA -- and a CTA whose SM is
+// still held by a concurrent kernel (the data-parallel step all-reduces gradient buckets under these GEMMs) starts
+// late by that kernel's whole duration; with the counter a late CTA simply finds nothing left.  The last CTA out
+// re-arms the counter for the next launch of the stream.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBigEpiWarps = 4;
 constexpr int kBigFirstEpiWarp = 2 + kConvWarps;
@@ -848,8 +854,24 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
   auto acc_full = [&](int a) { return bar_base + 8u * (4 * NS + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (4 * NS + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (4 * NS + 4);
+  constexpr int kSched = 4;                             // tile-id ring: producer -> MMA issuer, converters, epilogue
+  constexpr int kSchedReaders = 1 + kConvWarps + kBigEpiWarps;
+  auto sched_full = [&](int s) { return bar_base + 8u * (4 * NS + 5 + s); };
+  auto sched_empty = [&](int s) { return bar_base + 8u * (4 * NS + 5 + kSched + s); };
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(gen_base + (bar_base - base) + 8 * (4 * NS + 5 + 2 * kSched));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = grp.cta_start[grp.n];
+  int* const sched_ctr = grp.p[0].counters;             // [0] next tile, [1] CTAs that left
+  static_assert(kConvGroups == 2, "the converters split the K-block stream by parity");
+  // consumer side of the tile ring: the it-th tile of this CTA (-1: no more)
+  auto next_tile = [&](uint32_t it) {
+    const int s = (int)(it % kSched);
+    mbar_wait(sched_full(s), (it / kSched) & 1u);
+    const int t = sched_tile[s];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sched_empty(s));
+    return t;
+  };
 
   struct Tile { int pi, p0, q0, nkb; };
   auto decode = [&](int t) {
@@ -876,6 +898,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
       mbar_init(acc_full(a), 1);
       mbar_init(acc_empty(a), kBigEpiWarps);
     }
+    for (int k = 0; k < kSched; ++k) {
+      mbar_init(sched_full(k), 1);
+      mbar_init(sched_empty(k), kSchedReaders);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -891,9 +917,27 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
   pdl_trigger();
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    pdl_wait();
+    pdl_wait();   // (also orders this launch's draws from the tile counter behind the previous launch's re-arm)
     uint32_t g = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const bool dyn = ntiles > (int)gridDim.x;   // one tile per CTA: nothing to balance, no atomics
+    int t = blockIdx.x;
+    if (dyn) {
+      if (lane == 0) t = atomicAdd(sched_ctr, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+    }
+    for (uint32_t it = 0;; ++it) {
+      // publish tile `t` (or the end mark), then draw the one after it while this tile's K-blocks stream
+      const int ss = (int)(it % kSched);
+      if (it >= (uint32_t)kSched) mbar_wait(sched_empty(ss), ((it / kSched) & 1u) ^ 1u);
+      const bool live = t < ntiles;
+      if (lane == 0) {
+        sched_tile[ss] = live ? t : -1;
+        mbar_arrive(sched_full(ss));   // (release: the tile id is visible to whoever sees the phase complete)
+      }
+      __syncwarp();
+      if (!live) break;
+      int t_next = ntiles;
+      if (dyn && lane == 0) t_next = atomicAdd(sched_ctr, 1);
       const Tile tl = decode(t);
       const TcParams& prm = grp.p[tl.pi];
       for (int sg = 0; sg < prm.nseg; ++sg) {
@@ -910,12 +954,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
           __syncwarp();
         }
       }
+      t = __shfl_sync(0xffffffffu, t_next, 0);
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(kTileP >> 4) << 24);
     uint32_t g = 0, tc = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+    for (int t = next_tile(0); t >= 0; t = next_tile(++tc)) {
       const Tile tl = decode(t);
       const uint32_t ab = tc & 1u;
       if (tc >= 2u) mbar_wait(acc_empty(ab), ((tc >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator
@@ -945,12 +990,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
     }
   } else if (warp < kBigFirstEpiWarp) {
     // ============================== converters ==============================
-    uint32_t total = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) total += (uint32_t)decode(t).nkb;
     const int grp_id = (warp - 2) >> 2;
     const int gt = (threadIdx.x - 64) & (kGT - 1);
     auto split = [](float x, float& lo) { lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
-    for (uint32_t g = (uint32_t)grp_id; g < total; g += kConvGroups) {
+    uint32_t g = 0, tcount = 0;   // g: K-blocks of all earlier tiles of this CTA
+    for (int t = next_tile(0); t >= 0; t = next_tile(++tcount)) {
+    const uint32_t g_end = g + (uint32_t)decode(t).nkb;
+    for (g += (g + (uint32_t)grp_id) & 1u ? 1u : 0u; g < g_end; g += kConvGroups) {   // this group's K-blocks: g % 2 == grp_id
       const int s = (int)(g % NS);
       const uint32_t ph = (g / NS) & 1u;
       // Q: the raw tile doubles as the hi operand (kind::tf32 ignores the low 13 mantissa bits); lo goes to the sibling
@@ -990,6 +1036,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(conv_bar(s));
     }
+    g = g_end;
+    }
   } else {
     // ============================== epilogue ==============================
     pdl_wait();   // C, `add` and c_row_len may be produced by the preceding kernels
@@ -997,7 +1045,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
     float* stg = reinterpret_cast<float*>(gen_base + (epi_base - base)) + (warp - kBigFirstEpiWarp) * 32 * Cfg::kEpiPitch;
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;   // write-out: 8 lanes cover one 128-byte row segment
     uint32_t tc = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+    for (int t = next_tile(0); t >= 0; t = next_tile(++tc)) {
       const Tile tl = decode(t);
       const TcParams& prm = grp.p[tl.pi];
       const uint32_t ab = tc & 1u;
@@ -1094,6 +1142,15 @@ __global__ void __launch_bounds__(kBigThreads, 1) gemm_big_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    // every CTA has drawn its last tile before it gets here: the last one out re-arms the counters
+    __threadfence();
+    if (atomicAdd(sched_ctr + 1, 1) == (int)gridDim.x - 1) {
+      sched_ctr[0] = 0;
+      sched_ctr[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -1353,7 +1410,7 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
   }
   // library-owned scratch of this (device, stream): slabs, two counters per CTA (+ 16 bytes of zeros: TcParams::zero16)
   float* tc_scratch = static_cast<float*>(lib_scratch(kScratchTcSlabs, stream, sizeof(float) * (size_t)kScratchSlots * kTileP * 128, false));
-  int* tc_counters = static_cast<int*>(lib_scratch(kScratchTcCounters, stream, sizeof(int) * (2 * kScratchSlots + 4), true));
+  int* tc_counters = static_cast<int*>(lib_scratch(kScratchTcCounters, stream, sizeof(int) * (2 * kScratchSlots + 8), true));
   if (!tc_scratch || !tc_counters) return SET_ERR_CUDA;
   int cta = 0;
   for (int k = 0; k < grp.n; ++k) {
@@ -1413,7 +1470,11 @@ int gemm_tc_try_group(int mode, const GemmProblem* probs, int n, bool* taken, cu
     bool big_ok = big_on != 0;
     for (int k = 0; k < grp.n; ++k)
       big_ok = big_ok && !grp.p[k].fused && grp.p[k].split_k == 1 && !grp.p[k].swap && grp.p[k].nblk == 1;
-    if (big_ok && (++g_tc_twin_launches, true))
+    if (big_ok) {
+      ++g_tc_twin_launches;
+      small.p[0].counters = tc_counters + 2 * kScratchSlots + 4;   // tile counter + exit counter of the persistent kernel
+    }
+    if (big_ok)
       return launch_chain(gemm_big_kernel<G>, dim3(cta < g_sm_count ? cta : g_sm_count), dim3(kBigThreads),
                           BigCfg::kSmemBytes, stream, small);
     // many tiles per SM and no fused epilogue in play: two CTAs per SM (see TcCfg)

@@ -114,7 +114,7 @@ class DAEBase(nn.Module):
 
     FIELDS = DCNET_FIELDS
     STRUCT = SetDcNetParams
-    LATE_FIELDS = ()
+    BUCKET_FIELDS = ()
     # flat-parameter plumbing shared with EditNet
     _ordered_params = EditNetBase._ordered_params
     flatten_parameters = EditNetBase.flatten_parameters

@@ -344,8 +344,15 @@ class EditNetBase(nn.Module):
 
     FIELDS = EDITNET_FIELDS
     STRUCT = SetEditNetParams
-    LATE_FIELDS = ("embed", "enc_x2h_w", "enc_x2h_b", "enc_h2h_w", "enc_h2h_b", "enc_aff_w", "enc_aff_b",
-                   "va_emb_w", "va_emb_b", "va_feat_w", "va_feat_b")
+    # Gradient buckets of the data-parallel step, in the order the reverse pass finishes them (csrc/editnet.cu
+    # backward_core, include/set_b200.h set_backward_bucket_events); fields not listed form the last bucket.
+    BUCKET_FIELDS = (
+        ("fc_w", "fc_b"),
+        ("al_wih", "al_whh", "al_bih", "al_bhh",
+         "cl_x2h_w", "cl_x2h_b", "cl_h2h_w", "cl_h2h_b", "cl_gcn_w", "cl_gcn_b", "cl_gcm_w", "cl_gcm_b",
+         "ca_feat_w", "ca_feat_b"),
+        ("embed", "enc_x2h_w", "enc_x2h_b", "enc_h2h_w", "enc_h2h_b", "enc_aff_w", "enc_aff_b"),
+    )
 
     # ---- flat parameter storage: every parameter is a view into one buffer, so the optimizer
     # tail and the data-parallel all-reduce see a single tensor
@@ -359,17 +366,21 @@ class EditNetBase(nn.Module):
             base = self._flat.data_ptr()
             if all(p.data_ptr() == base + 4 * o for p, o in zip(params, self._offsets)):
                 return self._flat
-        # Layout of the flat buffer: the parameters whose gradients are final LAST in the reverse pass (embedding table,
-        # caption encoder, att_embed / features_att: LATE_FIELDS) come first, everything else behind them -- the early-
-        # final "tail" is then one contiguous range that a data-parallel step all-reduces underneath the rest of the
-        # reverse pass (train.py, set_backward_bucket_notify).
+        # Layout of the flat buffer: one contiguous range per gradient bucket, in the order the reverse pass finishes
+        # them (BUCKET_FIELDS, then everything else) -- a data-parallel step all-reduces each range underneath the rest of
+        # the reverse pass as soon as it is final (train.py, set_backward_bucket_events).
         names = [n for n, _ in self.FIELDS]
-        order = [names.index(n) for n in self.LATE_FIELDS] + [i for i, n in enumerate(names) if n not in self.LATE_FIELDS]
-        offs, total = [0] * len(params), 0
-        for i in order:
-            offs[i] = total
-            total += (params[i].numel() + 63) // 64 * 64
-        self._tail_offset = offs[order[len(self.LATE_FIELDS)]] if len(self.LATE_FIELDS) < len(params) else total
+        listed = [n for b in self.BUCKET_FIELDS for n in b]
+        groups = [list(b) for b in self.BUCKET_FIELDS] + [[n for n in names if n not in listed]]
+        groups = [g for g in groups if g]
+        offs, total, starts = [0] * len(params), 0, []
+        for g in groups:
+            starts.append(total)
+            for n in g:
+                i = names.index(n)
+                offs[i] = total
+                total += (params[i].numel() + 63) // 64 * 64
+        self._bucket_offsets = starts           # ascending; bucket k = flat[starts[k]:starts[k+1]] (last: to the end)
         flat = torch.zeros(total, device=dev, dtype=torch.float32)
         for p, o in zip(params, offs):
             view = flat[o:o + p.numel()].view(p.shape)

@@ -36,30 +36,45 @@ class XETrainer:
         self.step_count = 0
         self._state = None
         self._comm_stream = None
+        self._events = None
         self.gpu_launches_last_step = 0
 
-    def _tail_offset(self):
-        """first element of the gradient range that is final early in the reverse pass: everything behind the embedding
-        table, the caption encoder and att_embed / features_att in the flat layout (EditNetBase.flatten_parameters)"""
-        return self.decoder._tail_offset
+    def _bucket_events(self, n):
+        """n CUDA events the library records as the buckets become final (created once; recording them here forces
+        torch to create the underlying cudaEvent_t, whose handle the C ABI takes)"""
+        if self._events is None or len(self._events) != n:
+            self._events = [torch.cuda.Event() for _ in range(n)]
+            for ev in self._events:
+                ev.record()
+        return self._events
 
     def _allreduce_overlapped(self, grad, n, local_count, run_backward):
-        """run_backward() enqueues the reverse pass; the tail bucket (+ the count slot behind it) is all-reduced on a
-        side stream as soon as it is final, the head bucket after the pass.  Returns the count slot."""
+        """run_backward() enqueues the reverse pass.  The gradient buckets (contiguous ranges of the flat buffer in the
+        order the pass finishes them: EditNetBase.BUCKET_FIELDS) are all-reduced on a side stream, each as soon as the
+        library has recorded its event; only the last bucket (+ the count slot behind it) waits for the end of the
+        pass.  Returns the count slot."""
         main = torch.cuda.current_stream()
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=grad.device)
         comm = self._comm_stream
-        off = self._tail_offset()
+        starts = list(self.decoder._bucket_offsets)
         count_slot = grad[n:n + 1]
         count_slot.copy_(local_count.reshape(1).to(count_slot.dtype))
-        check(_lib.lib().set_backward_bucket_notify(C.c_void_p(comm.cuda_stream)))
-        run_backward()                                   # (records the event + makes `comm` wait, mid-pass)
+        evs = self._bucket_events(len(starts) - 1)
+        handles = (C.c_void_p * max(1, len(evs)))(*[ev.cuda_event for ev in evs])
+        check(_lib.lib().set_backward_bucket_events(handles, len(evs)))
+        run_backward()                                   # (records event k when bucket k is final)
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
         if multi:
+            import os
+            skip = int(os.environ.get("SET_DP_EXPERIMENT_SKIP", "0"))
             with torch.cuda.stream(comm):
-                dist.all_reduce(grad[off:n + 64], op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(grad[:off], op=dist.ReduceOp.SUM, group=self.group)
+                for k, ev in enumerate(evs):
+                    comm.wait_event(ev)
+                    if not (skip >> k) & 1:
+                        dist.all_reduce(grad[starts[k]:starts[k + 1]], op=dist.ReduceOp.SUM, group=self.group)
+            if not (skip >> len(evs)) & 1:
+                dist.all_reduce(grad[starts[-1]:n + 64], op=dist.ReduceOp.SUM, group=self.group)
             main.wait_stream(comm)
         return count_slot
 

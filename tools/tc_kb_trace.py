@@ -5,22 +5,25 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from show_edit_tell_b200 import _lib as L
 lib = L.lib()
-shapes = [(43776, 512, 1024), (1216, 10000, 1024), (2304, 1024, 2048)]
-for M, N, K in shapes:
+shapes = [(64, 1024, 1024, 1), (64, 3072, 4096, 0), (64, 1024, 4096, 1), (64, 1024, 8192, 1)]
+if len(sys.argv) > 1 and sys.argv[1] == "big":
+    shapes = [(43776, 512, 1024, 0), (1216, 10000, 1024, 0), (2304, 1024, 2048, 0)]
+    lib.set_gemm_big(0) if hasattr(lib, "set_gemm_big") else None
+for M, N, K, beta in shapes:
     A, W = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
     Cm = torch.zeros(M, N, device="cuda")
     buf = torch.zeros(16 + 4096, dtype=torch.int64, device="cuda")
     for it in range(3):
         buf.zero_()
         lib.set_gemm_trace(L.ptr(buf))
-        L.check(lib.set_gemm(0, M, N, K, L.ptr(A), K, L.ptr(W), K, None, L.ptr(Cm), N, 0, 0, None))
+        L.check(lib.set_gemm(0, M, N, K, L.ptr(A), K, L.ptr(W), K, None, L.ptr(Cm), N, beta, 0, None))
         torch.cuda.synchronize()
     lib.set_gemm_trace(None)
     ph = buf[:13].cpu().double()
     st = buf[16:16 + 2000:2].cpu().double(); en = buf[17:17 + 2000:2].cpu().double()
     live = st > 0
     g0 = float(st[live].min())
-    print("shape %dx%dx%d phase stamps of CTA 0 (us after the first CTA start): %s" % (M, N, K, " ".join(
+    print("shape %dx%dx%d beta %d phase stamps of CTA 0 (us after the first CTA start): %s" % (M, N, K, beta, " ".join(
         "%d:%.1f" % (i, (float(ph[i]) - g0) / 1e3) for i in range(13) if ph[i] > 0)))
     print("   CTAs traced %d: start min/median/max %.1f/%.1f/%.1f us, end min/median/max %.1f/%.1f/%.1f us" % (
         int(live.sum()), 0.0, (float(st[live].median()) - g0) / 1e3, (float(st[live].max()) - g0) / 1e3,
