@@ -351,11 +351,12 @@ SET_API int set_beam_finalize(int N, int K, int Lmax, int steps_done, const int*
                               float* out_score, void* stream);
 
 /* Data-parallel overlap (new: the reference is single-process).  The reverse pass finishes the parameter gradients in
- * four groups ("buckets"), in this order:
+ * five groups ("buckets"), in this order:
  *   0  fc.*                                                          before the per-step loop
  *   1  attention_lstm.*, copy_lstm.*, caption_attention.cap_features_att.*   after the loop (big weight-gradient groups)
  *   2  embed.*, caption_encoder.*                                    input-gradient tail, encoder BPTT
- *   3  everything else (caption / visual attention), final when the call returns.
+ *   3  the rest of caption_attention.*, visual_attention.decoder_att / full_att
+ *   4  visual_attention.features_att / att_embed, final when the call returns.
  * `events` = n <= 8 cudaEvent_t handles.  Arms the NEXT set_editnet_xe_backward / set_editnet_rollout_backward call of
  * this thread: the call records events[k] on its stream as soon as bucket k is final (events of buckets the call does
  * not know, and every event not recorded earlier, are recorded at its end).  A communication stream that waits for

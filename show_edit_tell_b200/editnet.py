@@ -352,6 +352,8 @@ class EditNetBase(nn.Module):
          "cl_x2h_w", "cl_x2h_b", "cl_h2h_w", "cl_h2h_b", "cl_gcn_w", "cl_gcn_b", "cl_gcm_w", "cl_gcm_b",
          "ca_feat_w", "ca_feat_b"),
         ("embed", "enc_x2h_w", "enc_x2h_b", "enc_h2h_w", "enc_h2h_b", "enc_aff_w", "enc_aff_b"),
+        ("ca_dec_w", "ca_dec_b", "ca_full_w", "ca_full_b", "ca_gate_w", "ca_gate_b", "ca_sc_w", "ca_sc_b",
+         "ca_tc_w", "ca_tc_b", "va_dec_w", "va_dec_b", "va_full_w", "va_full_b"),
     )
 
     # ---- flat parameter storage: every parameter is a view into one buffer, so the optimizer

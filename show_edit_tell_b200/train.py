@@ -27,7 +27,7 @@ from .parallel import allreduce_sums
 
 class XETrainer:
     def __init__(self, decoder, lr=5e-4, max_norm=0.25, betas=(0.9, 0.999), eps=1e-8, process_group=None,
-                 distributed=None, overlap=True):
+                 distributed=None, overlap=True, trace_overlap=False):
         self.decoder = decoder
         self.lr, self.max_norm, self.betas, self.eps = lr, max_norm, betas, eps
         self.distributed = dist.is_initialized() if distributed is None else distributed
@@ -37,13 +37,15 @@ class XETrainer:
         self._state = None
         self._comm_stream = None
         self._events = None
+        self.trace_overlap = trace_overlap   # debugging: time the buckets of the overlapped all-reduce
+        self._trace = None
         self.gpu_launches_last_step = 0
 
     def _bucket_events(self, n):
         """n CUDA events the library records as the buckets become final (created once; recording them here forces
         torch to create the underlying cudaEvent_t, whose handle the C ABI takes)"""
         if self._events is None or len(self._events) != n:
-            self._events = [torch.cuda.Event() for _ in range(n)]
+            self._events = [torch.cuda.Event(enable_timing=self.trace_overlap) for _ in range(n)]
             for ev in self._events:
                 ev.record()
         return self._events
@@ -52,7 +54,8 @@ class XETrainer:
         """run_backward() enqueues the reverse pass.  The gradient buckets (contiguous ranges of the flat buffer in the
         order the pass finishes them: EditNetBase.BUCKET_FIELDS) are all-reduced on a side stream, each as soon as the
         library has recorded its event; only the last bucket (+ the count slot behind it) waits for the end of the
-        pass.  Returns the count slot."""
+        pass.  Returns the count slot.  With `trace_overlap` the step also records when each bucket became final and
+        when its all-reduce ended (`overlap_timeline()`)."""
         main = torch.cuda.current_stream()
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=grad.device)
@@ -63,20 +66,39 @@ class XETrainer:
         evs = self._bucket_events(len(starts) - 1)
         handles = (C.c_void_p * max(1, len(evs)))(*[ev.cuda_event for ev in evs])
         check(_lib.lib().set_backward_bucket_events(handles, len(evs)))
+        tr = None
+        if self.trace_overlap:
+            tr = {"t0": torch.cuda.Event(enable_timing=True), "bwd_end": torch.cuda.Event(enable_timing=True),
+                  "final": evs, "ar_end": [torch.cuda.Event(enable_timing=True) for _ in range(len(starts))],
+                  "mb": [(b - a) * 4 / 1e6 for a, b in zip(starts, starts[1:] + [n + 64])]}
+            tr["t0"].record(main)
         run_backward()                                   # (records event k when bucket k is final)
+        if tr:
+            tr["bwd_end"].record(main)
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
         if multi:
-            import os
-            skip = int(os.environ.get("SET_DP_EXPERIMENT_SKIP", "0"))
             with torch.cuda.stream(comm):
                 for k, ev in enumerate(evs):
                     comm.wait_event(ev)
-                    if not (skip >> k) & 1:
-                        dist.all_reduce(grad[starts[k]:starts[k + 1]], op=dist.ReduceOp.SUM, group=self.group)
-            if not (skip >> len(evs)) & 1:
-                dist.all_reduce(grad[starts[-1]:n + 64], op=dist.ReduceOp.SUM, group=self.group)
+                    dist.all_reduce(grad[starts[k]:starts[k + 1]], op=dist.ReduceOp.SUM, group=self.group)
+                    if tr:
+                        tr["ar_end"][k].record(comm)
+            dist.all_reduce(grad[starts[-1]:n + 64], op=dist.ReduceOp.SUM, group=self.group)
+            if tr:
+                tr["ar_end"][-1].record(main)
             main.wait_stream(comm)
+        self._trace = tr if multi else None
         return count_slot
+
+    def overlap_timeline(self):
+        """(trace_overlap=True, after a step + synchronize) ms since the start of the reverse pass: when each bucket
+        became final, when its all-reduce ended, when the pass ended"""
+        tr = self._trace
+        if not tr:
+            return None
+        t0 = tr["t0"]
+        return {"bucket_mb": tr["mb"], "final_ms": [t0.elapsed_time(e) for e in tr["final"]] + [t0.elapsed_time(tr["bwd_end"])],
+                "allreduce_end_ms": [t0.elapsed_time(e) for e in tr["ar_end"]], "backward_end_ms": t0.elapsed_time(tr["bwd_end"])}
 
     def _ensure_state(self):
         flat = self.decoder.flatten_parameters()
