@@ -121,18 +121,35 @@ class XETrainer:
                 self.step_count = 0
         return flat, self._state
 
-    # optimizer checkpointing (the reference pickles the optimizer object, editnet.py:168-175)
+    # optimizer checkpointing (the reference pickles the optimizer object, editnet.py:168-175).  The moments are saved
+    # per parameter, keyed by the module's state_dict names -- the order of the flat buffer is an internal matter (it
+    # follows the gradient buckets) and must not leak into checkpoints.
     def state_dict(self):
         _, st = self._ensure_state()
-        return {"step": self.step_count, "exp_avg": st["m"].clone(), "exp_avg_sq": st["v"].clone(),
+        dec = self.decoder
+        views_m, views_v = dec._views(st["m"]), dec._views(st["v"])
+        keys = [key for _, key in dec.FIELDS]
+        return {"step": self.step_count,
+                "exp_avg": {k: m.clone() for k, m in zip(keys, views_m)},
+                "exp_avg_sq": {k: v.clone() for k, v in zip(keys, views_v)},
                 "lr": self.lr, "betas": self.betas, "eps": self.eps, "max_norm": self.max_norm}
 
     def load_state_dict(self, sd):
         _, st = self._ensure_state()
-        if sd["exp_avg"].numel() != st["n"]:
-            raise ValueError("optimizer state has %d elements, the model has %d" % (sd["exp_avg"].numel(), st["n"]))
-        st["m"].copy_(sd["exp_avg"])
-        st["v"].copy_(sd["exp_avg_sq"])
+        dec = self.decoder
+        keys = [key for _, key in dec.FIELDS]
+        for name, buf in (("exp_avg", st["m"]), ("exp_avg_sq", st["v"])):
+            src = sd[name]
+            if not isinstance(src, dict):
+                raise ValueError("optimizer state holds a flat %s tensor: written before the moments were keyed by "
+                                 "parameter name; its element order is unknown" % name)
+            missing = [k for k in keys if k not in src]
+            if missing:
+                raise ValueError("optimizer state lacks %s for %s" % (name, ", ".join(missing[:4])))
+            for k, view in zip(keys, dec._views(buf)):
+                if tuple(src[k].shape) != tuple(view.shape):
+                    raise ValueError("%s[%s] has shape %s, the parameter has %s" % (name, k, tuple(src[k].shape), tuple(view.shape)))
+                view.copy_(src[k])
         self.step_count = int(sd["step"])
         self.lr, self.betas, self.eps = sd.get("lr", self.lr), tuple(sd.get("betas", self.betas)), sd.get("eps", self.eps)
         self.max_norm = sd.get("max_norm", self.max_norm)

@@ -386,6 +386,38 @@ def test_trainer_step_matches_oracle_step(small_sd, small_cfg):
         assert ((got - p).abs() * big).max() < 5e-6, k
 
 
+def test_trainer_checkpoint_resumes(small_sd, small_cfg):
+    """optimizer state saved per parameter name (reference: the pickled optimizer of editnet.py:168-175): a trainer
+    rebuilt from model + optimizer checkpoints continues like the one that kept running (to the run-to-run noise of the
+    split-K reductions)"""
+    _lib, editnet, editnet_rl, editnet_adaptive, trainmod, U = _imports()
+    c = small_cfg
+    batches = [_cuda(synth.make_batch(c["B"], c["V"], c["R"], c["Fdim"], c["cap_width"], c["prev_width"], ragged=True,
+                                      seed=60 + i, min_len=3, min_prev=2), XE_KEYS) for i in range(4)]
+    mod, _ = U.build_module(editnet.DecoderC, small_sd, c["V"], c["D"], c["A"], c["Fdim"])
+    tr = trainmod.XETrainer(mod, distributed=False)
+    for i in range(2):
+        tr.step(*batches[i], seed=100 + i)
+    model_sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    opt_sd = tr.state_dict()
+    assert set(opt_sd["exp_avg"]) == {k for _, k in _lib.EDITNET_FIELDS}
+    for k, v in opt_sd["exp_avg"].items():
+        assert tuple(v.shape) == tuple(mod.get_parameter(k).shape), k
+    mod2, _ = U.build_module(editnet.DecoderC, {k: v.cpu() for k, v in model_sd.items()}, c["V"], c["D"], c["A"], c["Fdim"])
+    tr2 = trainmod.XETrainer(mod2, distributed=False)
+    tr2.load_state_dict(opt_sd)
+    for i in range(2, 4):
+        la, lb = tr.step(*batches[i], seed=100 + i), tr2.step(*batches[i], seed=100 + i)
+        assert abs(float(la) - float(lb)) < 1e-5
+    for (k, a), (_, b) in zip(mod.state_dict().items(), mod2.state_dict().items()):
+        # (an element whose gradient is at the noise level of the split-K reductions may move by up to lr per step in
+        # either run -- Adam normalises by |g|; wrongly restored moments would move EVERY element by that much)
+        d = (a.float() - b.float()).abs()
+        assert float(d.max()) < 2.5e-3 and float(d.mean()) < 2e-6, (k, float(d.max()), float(d.mean()))
+    with pytest.raises(ValueError):
+        tr2.load_state_dict({"step": 1, "exp_avg": torch.zeros(3), "exp_avg_sq": torch.zeros(3)})
+
+
 def test_caption_encoder_entry_and_adaptive_six_tuple(small_sd, small_cfg):
     _lib, editnet, editnet_rl, editnet_adaptive, trainmod, U = _imports()
     c = small_cfg
