@@ -371,8 +371,9 @@ SET_API int set_step_geometry(int* grid, int* cluster);
 /* debugging: device buffer of >= steps * 8 * grid uint64; every CTA stamps %globaltimer at each phase boundary of each
    timestep: [(step * 8 + phase) * grid + cta], phases 0..6 = end of A, B, C1, C2, D, E, F.  NULL switches it off. */
 SET_API int set_step_trace(void* buf);
-/* tensor-core launches that took the two-CTAs-per-SM ("twin") configuration since the last reset (parity tests
-   assert that the big time-batched GEMMs of the benchmarked configuration really ran on it) */
+/* tensor-core launches that took one of the many-tile configurations -- the persistent kernel of the big time-batched
+   GEMMs (gemm_big_kernel) or the two-CTAs-per-SM ("twin") launch -- since the last reset (parity tests assert that the
+   big time-batched GEMMs of the benchmarked configuration really ran on them) */
 SET_API long long set_gemm_twin_launches(int reset);
 /* C = A @ B^T style contraction through the library's GEMM engine (mode 0 NT, 1 NN, 2 TN). */
 SET_API int set_gemm(int mode, int M, int N, int K, const float* A, long lda, const float* Bm, long ldb,
