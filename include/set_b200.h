@@ -363,6 +363,12 @@ SET_API int set_beam_finalize(int N, int K, int Lmax, int steps_done, const int*
  * events[k] before all-reducing bucket k overlaps the collective with the rest of the pass; the Python side
  * (train.XETrainer) keeps each bucket contiguous in its flat gradient buffer. */
 SET_API int set_backward_bucket_events(void* const* events, int n);
+/* Arms the NEXT set_editnet_xe_backward / set_editnet_rollout_backward call of this thread to INITIALISE the gradient
+ * buffers instead of accumulating into them: weight-matrix gradients are written with beta = 0 and the accumulated /
+ * scattered ones (biases, embedding table, the full_att rows) are zeroed by the call itself -- the caller need not
+ * zero anything (trainers: saves a 355 MB memset and the read of every old gradient per step).  Default (not armed):
+ * gradients accumulate, as autograd expects. */
+SET_API int set_backward_overwrite_grads(int on);
 /* persistent decode-step kernel (csrc/step_kernel.cu): launches since the last reset and the timesteps they covered
    (0 launches: the shape fell outside the persistent path and the per-step launch chain ran) */
 SET_API int set_step_stats(long long* launches, long long* steps, int reset);

@@ -180,6 +180,7 @@ _SIGS = {
     "set_gemm_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
     "set_gemm_twin_launches": (C.c_longlong, [C.c_int]),
     "set_backward_bucket_events": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "set_backward_overwrite_grads": (C.c_int, [C.c_int]),
     "set_beam_expand": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P, _P]),
     "set_beam_gather": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -908,6 +908,10 @@ __global__ void sum_time_kernel(const float* __restrict__ x, float* __restrict__
     out[y] = s;
   }
 }
+__global__ void zero_batch_kernel(const ZeroBatch zb) {
+  const ZeroJob j = zb.j[blockIdx.y];
+  for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < j.n; y += (long)gridDim.x * blockDim.x) j.p[y] = 0.f;
+}
 __global__ void keep_mask_kernel(float* __restrict__ out, long n, uint64_t seed, uint32_t site, long base) {
   for (long y = (long)blockIdx.x * blockDim.x + threadIdx.x; y < n; y += (long)gridDim.x * blockDim.x)
     out[y] = drop_keep(seed, site, (uint64_t)(base + y)) ? 1.f : 0.f;
@@ -1142,6 +1146,18 @@ int transpose_batch(const TrJob* jobs, int n, cudaStream_t s) {
 }
 int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s) {
   sum_time_kernel<<<blocks_for(BN, kThreads), kThreads, 0, s>>>(x, out, T, BN);
+  LAUNCH_OK();
+}
+int zero_batch(const ZeroJob* jobs, int n, cudaStream_t s) {
+  if (n <= 0) return SET_OK;
+  if (n > kZeroMaxJobs) { set_record_error("zero_batch: too many ranges"); return SET_ERR_ARG; }
+  ZeroBatch zb;
+  long longest = 0;
+  for (int k = 0; k < n; ++k) { zb.j[k] = jobs[k]; longest = jobs[k].n > longest ? jobs[k].n : longest; }
+  for (int k = n; k < kZeroMaxJobs; ++k) zb.j[k] = ZeroJob{nullptr, 0};
+  int bx = blocks_for(longest, kThreads);
+  if (bx > 1184) bx = 1184;
+  zero_batch_kernel<<<dim3(bx, n), kThreads, 0, s>>>(zb);
   LAUNCH_OK();
 }
 int dropout_keep_mask(float* out, long n, uint64_t seed, uint32_t site, long base, cudaStream_t s) {

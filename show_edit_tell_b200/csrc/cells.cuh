@@ -149,6 +149,11 @@ struct TrBatch { int n; TrJob j[kTrMaxJobs]; };
 int transpose_batch(const TrJob* jobs, int n, cudaStream_t s);
 // sum over time of a [T][B][N] buffer -> [B][N]
 int sum_time(const float* x, float* out, int T, long BN, cudaStream_t s);
+// several ranges set to zero in one launch (the accumulated / scattered gradient tensors of an overwriting reverse pass)
+constexpr int kZeroMaxJobs = 40;
+struct ZeroJob { float* p; long n; };
+struct ZeroBatch { ZeroJob j[kZeroMaxJobs]; };
+int zero_batch(const ZeroJob* jobs, int n, cudaStream_t s);
 // materialise keep bits as floats (tests): out[i] = keep(seed, site, base+i)
 int dropout_keep_mask(float* out, long n, uint64_t seed, uint32_t site, long base, cudaStream_t s);
 

@@ -605,6 +605,12 @@ int steps_persistent(Ctx& c, const float* feats, int t0, int nt, const int* bt, 
 // (tools/dp_timeline.py): every overlapped all-reduce ends well before the next bucket is final; what the overlap
 // costs is the SMs and memory bandwidth the collective takes from the kernels it runs beside (the pass is ~0.4 ms
 // longer than on one GPU).
+// Overwriting reverse pass (set_backward_overwrite_grads): the next backward call initialises the gradient tensors
+// itself -- every weight matrix is written by exactly one GEMM (or by GEMMs on disjoint column blocks), so those run
+// with beta = 0; only the tensors that are accumulated or scattered into (biases, the embedding table, the two full_att
+// rows) are zeroed, in one small launch.  Saves the caller's memset of the whole flat buffer (355 MB) and the
+// read-modify-write of every weight gradient.
+thread_local bool g_overwrite_armed = false;
 constexpr int kMaxBuckets = 8;
 thread_local cudaEvent_t g_bucket_ev[kMaxBuckets];
 thread_local int g_bucket_n = 0;       // events armed for the next reverse pass
@@ -637,6 +643,18 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
   cudaStream_t st = c.st;
   const int TB = T * B;
   struct BucketGuard { ~BucketGuard() { g_bucket_n = g_bucket_next = 0; } } bucket_guard;   // an error return disarms too
+  const bool overwrite = g_overwrite_armed;
+  g_overwrite_armed = false;
+  if (overwrite) {
+    const ZeroJob zj[] = {
+        {g.embed, (long)V * D}, {g.enc_x2h_b, 4L * D}, {g.enc_h2h_b, 4L * D}, {g.enc_aff_b, D}, {g.ca_feat_b, A},
+        {g.ca_dec_b, A}, {g.ca_full_w, A}, {g.ca_full_b, 1}, {g.ca_gate_b, D}, {g.ca_sc_b, D}, {g.ca_tc_b, D},
+        {g.va_emb_b, D}, {g.va_feat_b, A}, {g.va_dec_b, A}, {g.va_full_w, A}, {g.va_full_b, 1}, {g.al_bih, 4L * D},
+        {g.al_bhh, 4L * D}, {g.cl_x2h_b, 4L * D}, {g.cl_h2h_b, 4L * D}, {g.cl_gcn_b, D}, {g.cl_gcm_b, D}, {g.fc_b, V},
+        {g.al_whh, T > 1 ? 0L : 4L * D * D}};   // (no recurrent step: nothing writes d W_hh)
+    SET_PROPAGATE(zero_batch(zj, (int)(sizeof(zj) / sizeof(zj[0])), st));
+  }
+  const int wbeta = overwrite ? 0 : 1;   // beta of every weight-gradient GEMM
   SET_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(s.emb_prev) + s.regionB_begin, 0,
                                  s.regionB_end - s.regionB_begin, st));
   // The dX pass contracts over a weight's OUTPUT features.  The tensor-core kernel wants both operands
@@ -699,7 +717,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
     } else {
       gemm_add_seg(p, dY, ldy, X, ldx, K);
     }
-    p.beta = 1;
+    p.beta = wbeta;
     return p;
   };
   {  // d(dropout(h2)) for every step at once: dlogits @ fc.weight
@@ -723,7 +741,7 @@ int backward_core(Ctx& c, const SetEditNetParams& g, const float* feats, const i
       for (int k = 0; k < 2; ++k) {
         q[k] = k == 0 ? gemm_problem(V, D, g.fc_w, D) : gemm_problem(V, 1, g.fc_b, 1);
         gemm_add_seg(q[k], dl.p, dl.ld, k == 0 ? s.h2drop : s.ones, k == 0 ? D : 1, TB);
-        q[k].beta = 1;
+        q[k].beta = (k == 0) ? wbeta : 1;   // (fc.bias is zeroed with the other biases)
         q[k].a_inner = dl.inner; q[k].a_ld_inner = dl.ld_inner; q[k].a_row_len = dl.row_len; q[k].a_valid_inner = B;
       }
       SET_PROPAGATE(gemm_group(kTN, q, 2, st));
@@ -1347,6 +1365,11 @@ int set_step_stats(long long* launches, long long* steps, int reset) {
   if (launches) *launches = g_step_launches;
   if (steps) *steps = g_step_steps;
   if (reset) g_step_launches = g_step_steps = 0;
+  return SET_OK;
+}
+
+int set_backward_overwrite_grads(int on) {
+  g_overwrite_armed = on != 0;
   return SET_OK;
 }
 

@@ -176,10 +176,12 @@ class XETrainer:
         check(L.set_editnet_xe_loss_time_major(C.byref(call.dims), C.byref(s), ptr(call.caps), inv, ptr(st["loss"]),
                                                ptr(call.ws), call.ws.numel(), _stream()))
         grad = st["grad"]
-        grad.zero_()
         g = dec._struct_for(grad[:st["n"]])
 
         def run_backward():
+            # the reverse pass initialises the gradient buffer itself (no 355 MB memset, no read of old gradients);
+            # the padding between parameters and the slots behind them are never written and stay zero
+            check(L.set_backward_overwrite_grads(1))
             check(L.set_editnet_xe_backward(
                 C.byref(call.dims), C.byref(s), C.byref(dec._struct), C.byref(g), ptr(call.feats), ptr(call.caps),
                 call.dec_host, ptr(call.prev), ptr(call.prev_len), call.seed, None, ptr(call.ws), call.ws.numel(),
@@ -261,11 +263,11 @@ class SCSTTrainer:
         check(L.set_reward_criterion(seq.shape[0], seq.shape[1], ptr(slp), ptr(seq), ptr(reward), ptr(st["loss"]),
                                      ptr(dlp), _stream()))
         grad = st["grad"]
-        grad.zero_()
         if self.distributed:
             # ranks contribute sums over their rows: undo the local 1/sum(mask), carry the mask count along
             mask_sum = torch.cat([torch.ones_like(seq[:, :1]), (seq[:, :-1] > 0).long()], 1).sum().float()
             dlp.mul_(mask_sum)
+        check(L.set_backward_overwrite_grads(1))     # (the reverse pass initialises the gradient buffer itself)
         dec._rollout_backward_raw(call, dlp, grad[:st["n"]])
         count_dev = None
         if self.distributed:
