@@ -419,19 +419,24 @@ class EditNetBase(nn.Module):
         anyway) spares the device->host read of the lengths, i.e. the one host sync of a step."""
         self._require_cuda(image_features)
         self.flatten_parameters()
+        take = lambda x: x[sort_ind]
         if host_lengths is not None:
             lens_h, sort_h = host_lengths[0].reshape(-1).sort(dim=0, descending=True, stable=True)
             sort_ind = sort_h.to(image_features.device, non_blocking=True)
             host = (lens_h - 1).tolist() + [int(host_lengths[1].max())]
+            if bool((sort_h == torch.arange(sort_h.numel())).all()):
+                # already in descending-length order (fixed-length or bucketed batches): the five gathers of the sort
+                # (editnet.py:488-493) are identity copies -- skipped
+                take = lambda x: x
         else:
             lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True, stable=True)  # editnet.py:488 (stable: ties as on CPU)
             host = None
         call = _Call()
-        call.feats = image_features[sort_ind].contiguous().float()
-        call.image_mean = None if image_mean is None else image_mean[sort_ind].contiguous().float()
-        call.caps = encoded_captions[sort_ind].contiguous()
-        call.prev = encoded_previous_captions[sort_ind].contiguous()
-        call.prev_len = previous_cap_length[sort_ind].contiguous().view(-1)
+        call.feats = take(image_features).contiguous().float()
+        call.image_mean = None if image_mean is None else take(image_mean).contiguous().float()
+        call.caps = take(encoded_captions).contiguous()
+        call.prev = take(encoded_previous_captions).contiguous()
+        call.prev_len = take(previous_cap_length).contiguous().view(-1)
         if host is None:
             host = torch.cat([lens - 1, call.prev_len.max().view(1)]).tolist()            # one D2H sync
         call.decode_lengths = host[:-1]
