@@ -16,10 +16,11 @@ dec = editnet.DecoderC(synth.word_map(V), D, D, D, A, FD).to(dev)
 tr = XETrainer(dec)
 b = synth.make_batch(B, V, R, FD, CAPW, PREVW, ragged=False, seed=100)
 args = [b[k].to(dev) for k in ("feats", "caps", "caplens", "prev", "prev_len")]
+hl = (b["caplens"], b["prev_len"])      # the loader's host copies of the lengths, as bench.py passes them
 for _ in range(3):
-    tr.step(*args)
+    tr.step(*args, host_lengths=hl)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-tr.step(*args)
+tr.step(*args, host_lengths=hl)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
