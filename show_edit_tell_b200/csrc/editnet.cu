@@ -623,6 +623,9 @@ int bucket_notify(int k, cudaStream_t st) {
   }
   return SET_OK;
 }
+// first statement of the backward entry points: whatever armed the call (bucket events, overwrite mode) is disarmed when
+// the call returns, on error paths that never reach backward_core too
+struct BackwardArms { ~BackwardArms() { g_overwrite_armed = false; g_bucket_n = g_bucket_next = 0; } };
 int bucket_finish(cudaStream_t st) {   // end of the pass: whatever was not signalled is final now; disarm
   const int r = bucket_notify(kMaxBuckets, st);
   g_bucket_n = g_bucket_next = 0;
@@ -1196,6 +1199,7 @@ int set_editnet_xe_backward(const SetDims* dims, const SetSeqShape* shape, const
                             const int* decode_len_host, const int64_t* prev, const int64_t* prev_len,
                             uint64_t seed, const float* d_predictions, void* workspace,
                             size_t workspace_bytes, void* stream) {
+  BackwardArms arms_guard;
   Ctx c;
   SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
   SET_REQUIRE(grads && feats && caps && decode_len_host && prev && prev_len, "null input");
@@ -1287,6 +1291,7 @@ int set_editnet_rollout_backward(const SetDims* dims, const SetSeqShape* shape, 
                                  const SetEditNetParams* grads, const float* feats, const int64_t* prev,
                                  const int64_t* prev_len, uint64_t seed, const float* d_seq_logprobs,
                                  void* workspace, size_t workspace_bytes, void* stream) {
+  BackwardArms arms_guard;
   Ctx c;
   SET_PROPAGATE(make_ctx(c, dims, shape, w, workspace, workspace_bytes, seed, stream));
   SET_REQUIRE(shape->train, "rollout backward needs a train-mode forward (activations kept)");
