@@ -7,8 +7,9 @@ from show_edit_tell_b200 import _lib as L
 lib = L.lib()
 shapes = [(64, 1024, 1024, 1), (64, 3072, 4096, 0), (64, 1024, 4096, 1), (64, 1024, 8192, 1)]
 if len(sys.argv) > 1 and sys.argv[1] == "big":
+    # the time-batched shapes; run with SET_TC_BIG=0 to trace the one-tile-per-CTA kernels (the persistent kernel keeps
+    # no per-K-block stamps)
     shapes = [(43776, 512, 1024, 0), (1216, 10000, 1024, 0), (2304, 1024, 2048, 0)]
-    lib.set_gemm_big(0) if hasattr(lib, "set_gemm_big") else None
 for M, N, K, beta in shapes:
     A, W = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
     Cm = torch.zeros(M, N, device="cuda")
